@@ -1,0 +1,128 @@
+// common.cuh -- shared types and device helpers of the B200 symmetric-ICP path.
+//
+// Data layout in HBM (DESIGN.md "Layout"): every cloud set is a batch of `nseg` independent
+// clouds ("segments"; a single pair is nseg = 1) stored with a fixed pitch of P points:
+//   pts[seg*P + j]  float4  Morton-sorted point j of the segment, .w = original index bits
+//   nrm[seg*P + j]  float4  (nx, ny, nz, curvature) of the same sorted point
+//   boxes[seg*nodes_per_seg + level_off[l] + i]  tight AABB of node i at level l of the implicit
+//       F-ary hierarchy over the sorted points (level 0 = groups of LEAF consecutive points)
+// Rounding contract: distances and transforms use separately rounded fp32
+// mul/add (no FMA) so that the CPU oracle computes bit-identical values.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define ICP_LOG_LEAF 3
+#define ICP_LEAF (1 << ICP_LOG_LEAF)     // points per leaf group (8 * 16 B = one 128 B line)
+#define ICP_LOG_FAN 3
+#define ICP_FAN (1 << ICP_LOG_FAN)       // children per node
+#define ICP_MAX_LEVELS 12
+#define ICP_NSUMS 37
+#define ICP_PART_STRIDE 40               // doubles per partial-sum row (37 padded)
+#define ICP_INVALID_ID 0x7fffffff
+
+struct __align__(32) Box {
+    float4 lo;  // .w unused
+    float4 hi;
+};
+
+// shape of the implicit hierarchy, identical for every segment of a cloud set
+struct TreeShape {
+    uint32_t pitch;                       // P: points per segment (multiple of ICP_LEAF)
+    uint32_t n_levels;                    // levels above and including the leaf-group level; root = n_levels-1
+    uint32_t level_off[ICP_MAX_LEVELS];   // offset of level l inside a segment's node array
+    uint32_t level_cnt[ICP_MAX_LEVELS];   // padded node count of level l (multiple of ICP_FAN, root = 1)
+    uint32_t nodes_per_seg;
+};
+
+// device view of a cloud set
+struct CloudView {
+    const float4* pts;
+    const float4* nrm;
+    const Box* boxes;
+    const uint32_t* pos_of_orig;          // seg*P + original index -> sorted position
+    const uint32_t* counts;               // points per segment
+    TreeShape shape;
+    uint32_t nseg;
+};
+
+// per-pair loop state, lives in device memory for the whole registration
+struct SegState {
+    double T[12];        // accumulated source->target transform, 3x4 row-major, fp64
+    float Tf[12];        // fp32 copy actually applied to the points
+    double origin[3];    // fixed origin of the raw sums (target bbox centre)
+    double diff, prev_diff, sumd2, min_ratio;
+    unsigned long long pairs;
+    int iter;            // solves applied
+    int searches;        // searches run
+    int done;            // 0 = running
+    int converged;       // 1 diff<=thr, 2 rel tol, 0 max iters
+    int degenerate;
+    int pad;
+};
+
+struct LoopParams {
+    int max_iters;
+    float diff_threshold;
+    double rel_diff_tol;
+    float max_pair_d2;   // +inf = off
+    int identity_pairs;
+    int warm_start;
+    int trace;
+};
+
+// ---- pinned fp32 arithmetic -------------------------------------------------------------
+__device__ __forceinline__ float dist2_rn(float px, float py, float pz, float qx, float qy, float qz) {
+    float dx = __fsub_rn(px, qx), dy = __fsub_rn(py, qy), dz = __fsub_rn(pz, qz);
+    return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
+
+// lower bound of dist2_rn from (qx,qy,qz) to any point inside the box.  Same operation order as
+// dist2_rn: every step is monotone under round-to-nearest, so bound <= member distance exactly.
+__device__ __forceinline__ float box_dist2_rn(const float4& lo, const float4& hi, float qx, float qy, float qz) {
+    float ex = fmaxf(fmaxf(__fsub_rn(lo.x, qx), __fsub_rn(qx, hi.x)), 0.f);
+    float ey = fmaxf(fmaxf(__fsub_rn(lo.y, qy), __fsub_rn(qy, hi.y)), 0.f);
+    float ez = fmaxf(fmaxf(__fsub_rn(lo.z, qz), __fsub_rn(qz, hi.z)), 0.f);
+    return __fadd_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)), __fmul_rn(ez, ez));
+}
+
+// x' = (((T0*x)+(T1*y))+(T2*z))+T3, no FMA.  T is 3x4 row-major.
+__device__ __forceinline__ float3 apply_rn(const float* __restrict__ T, float x, float y, float z) {
+    float3 r;
+    r.x = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(T[0], x), __fmul_rn(T[1], y)), __fmul_rn(T[2], z)), T[3]);
+    r.y = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(T[4], x), __fmul_rn(T[5], y)), __fmul_rn(T[6], z)), T[7]);
+    r.z = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(T[8], x), __fmul_rn(T[9], y)), __fmul_rn(T[10], z)), T[11]);
+    return r;
+}
+__device__ __forceinline__ float3 rotate_rn(const float* __restrict__ T, float x, float y, float z) {
+    float3 r;
+    r.x = __fadd_rn(__fadd_rn(__fmul_rn(T[0], x), __fmul_rn(T[1], y)), __fmul_rn(T[2], z));
+    r.y = __fadd_rn(__fadd_rn(__fmul_rn(T[4], x), __fmul_rn(T[5], y)), __fmul_rn(T[6], z));
+    r.z = __fadd_rn(__fadd_rn(__fmul_rn(T[8], x), __fmul_rn(T[9], y)), __fmul_rn(T[10], z));
+    return r;
+}
+
+// order-preserving float <-> uint map for atomicMin/Max on floats
+__device__ __forceinline__ uint32_t float_to_ordered(float f) {
+    uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__host__ __device__ __forceinline__ float ordered_to_float(uint32_t u) {
+    uint32_t v = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(v);
+#else
+    float f;
+    memcpy(&f, &v, 4);
+    return f;
+#endif
+}
+
+__device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
+
+#define ICP_CUDA_CHECK(expr)                                                        \
+    do {                                                                            \
+        cudaError_t _e = (expr);                                                    \
+        if (_e != cudaSuccess) return icp_fail(ctx, _e, #expr, __FILE__, __LINE__); \
+    } while (0)

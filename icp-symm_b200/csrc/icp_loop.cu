@@ -1,0 +1,725 @@
+// icp_loop.cu -- the registration loop of MyICP::RegisterSymm (ICP/myicp.cpp:100-150) on device.
+//
+// One iteration = two kernels on the context stream:
+//   nn_accum_kernel  (K1)  for every source point: apply the accumulated transform on load
+//                          (applyTransform, func.cpp:104-121, never materialised), exact nearest
+//                          neighbour in the target hierarchy (the search myicp.cpp:128-131 leaves
+//                          as a todo), evalDiff term (func.cpp:19-40), and the per-pair rows
+//                          m = (p+q) x n, n = n_p+n_q, c = (p-q).n of calculateMatrixNotation
+//                          (func.cpp:43-60) folded straight into the 27 unique normal-equation
+//                          sums (+ centroid, diff and count terms: 37 values), reduced by warp
+//                          shuffles and one fp64 partial row per block.
+//   solve_kernel     (K2)  fixed-order fp64 reduction of the partial rows, the loop test of
+//                          myicp.cpp:123, re-centring to the pair centroids, the 6x6 solve that
+//                          replaces the two JacobiSVD least-squares solves (func.cpp:64-73,87-88),
+//                          theta = atan|a| and the half-rotation composition (func.cpp:91-99, in
+//                          the order of the comment at :94), transform = incre * transform
+//                          (myicp.cpp:138).
+// The whole loop ((max_iters+1) x [K1,K2]) is captured once as a CUDA graph; a device-side `done`
+// flag in SegState turns the remaining launches into early exits once a pair has converged.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+#include "internal.h"
+#include "search.cuh"
+
+namespace {
+
+constexpr int kNNThreads = 256;
+constexpr int kNNWarps = kNNThreads / 32;
+constexpr int kSolveThreads = 512;
+constexpr int kSolveParts = kSolveThreads / ICP_NSUMS;  // 13
+
+struct NNParams {
+    CloudView src, tgt;
+    SegState* state;
+    const LoopParams* lp;
+    uint32_t* corr_pos;
+    double* partial;
+    uint32_t blocks_per_seg;
+    int shard_rank, shard_world;
+};
+
+struct SolveParams {
+    SegState* state;
+    const LoopParams* lp;
+    const double* partial;
+    double* gsum;
+    const uint32_t* src_counts;
+    float* trace_T;
+    double* trace_diff;
+    uint32_t blocks_per_seg;
+    int trace_stride;
+    int mode;  // 0 reduce+solve, 1 reduce only (-> gsum), 2 solve from gsum, 3 reduce + record, no solve
+};
+
+struct InitArgs {
+    float T[12];
+    double origin[3];
+    int has_T, has_origin;
+};
+
+__global__ void set_lp_kernel(LoopParams* dst, LoopParams v) { *dst = v; }
+
+__global__ void init_state_kernel(SegState* state, uint32_t nseg, InitArgs a, const float4* __restrict__ bb_lo,
+                                  const float4* __restrict__ bb_hi) {
+    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nseg) return;
+    SegState st;
+    memset(&st, 0, sizeof st);
+    for (int i = 0; i < 12; i++) {
+        float v = a.has_T ? a.T[i] : ((i % 5 == 0) ? 1.f : 0.f);
+        st.T[i] = (double)v;
+        st.Tf[i] = v;
+    }
+    float4 lo = bb_lo[s], hi = bb_hi[s];
+    // the origin of the raw sums must be exactly representable in fp32 (K1 subtracts it in fp32)
+    st.origin[0] = a.has_origin ? (double)(float)a.origin[0] : (double)(0.5f * (lo.x + hi.x));
+    st.origin[1] = a.has_origin ? (double)(float)a.origin[1] : (double)(0.5f * (lo.y + hi.y));
+    st.origin[2] = a.has_origin ? (double)(float)a.origin[2] : (double)(0.5f * (lo.z + hi.z));
+    st.min_ratio = 1.0;
+    state[s] = st;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1: search + accumulate
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kNNThreads) nn_accum_kernel(const __grid_constant__ NNParams P) {
+    const uint32_t seg = blockIdx.x / P.blocks_per_seg;
+    const uint32_t blk = blockIdx.x - seg * P.blocks_per_seg;
+    const SegState* st = P.state + seg;
+    __shared__ float sT[12];
+    __shared__ float sO[3];
+    __shared__ double wacc[kNNWarps][ICP_NSUMS];
+    __shared__ int sDone;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) sDone = st->done;
+    if (tid < 12) sT[tid] = st->Tf[tid];
+    if (tid < 3) sO[tid] = (float)st->origin[tid];
+    for (int v = tid; v < kNNWarps * ICP_NSUMS; v += kNNThreads) (&wacc[0][0])[v] = 0.0;
+    __syncthreads();
+    if (sDone) return;
+
+    const LoopParams lp = *P.lp;
+    const uint32_t ns = P.src.counts[seg], nt = P.tgt.counts[seg];
+    uint32_t qlo = 0, qhi = ns;
+    if (P.shard_world > 1) {
+        qlo = (uint32_t)(((unsigned long long)ns * (unsigned)P.shard_rank) / (unsigned)P.shard_world);
+        qhi = (uint32_t)(((unsigned long long)ns * (unsigned)(P.shard_rank + 1)) / (unsigned)P.shard_world);
+    }
+    const float4* __restrict__ spts = P.src.pts + (size_t)seg * P.src.shape.pitch;
+    const float4* __restrict__ snrm = P.src.nrm + (size_t)seg * P.src.shape.pitch;
+    const float4* __restrict__ tpts = P.tgt.pts + (size_t)seg * P.tgt.shape.pitch;
+    const float4* __restrict__ tnrm = P.tgt.nrm + (size_t)seg * P.tgt.shape.pitch;
+    const Box* __restrict__ tbox = P.tgt.boxes + (size_t)seg * P.tgt.shape.nodes_per_seg;
+    uint32_t* corr = P.corr_pos + (size_t)seg * P.src.shape.pitch;
+    const uint32_t ntiles = (qhi - qlo + kNNThreads - 1) / kNNThreads;
+
+    for (uint32_t tile = blk; tile < ntiles; tile += P.blocks_per_seg) {
+        const uint32_t i = qlo + tile * kNNThreads + tid;
+        float v[ICP_NSUMS];
+#pragma unroll
+        for (int k = 0; k < ICP_NSUMS; k++) v[k] = 0.f;
+        if (i < qhi && nt > 0) {
+            const float4 s = ldg4(spts + i);
+            const float3 p = apply_rn(sT, s.x, s.y, s.z);
+            Best b;
+            best_init(b);
+            if (lp.identity_pairs) {
+                uint32_t pos = P.tgt.pos_of_orig[(size_t)seg * P.tgt.shape.pitch + __float_as_uint(s.w)];
+                best_offer(b, ldg4(tpts + pos), pos, p.x, p.y, p.z);
+            } else {
+                uint32_t prev = lp.warm_start ? corr[i] : 0xffffffffu;
+                if (prev < nt) best_offer(b, ldg4(tpts + prev), prev, p.x, p.y, p.z);
+                else greedy_descent(P.tgt.shape, tbox, tpts, p.x, p.y, p.z, b);
+                nn_traverse(P.tgt.shape, tbox, tpts, p.x, p.y, p.z, b);
+            }
+            corr[i] = b.pos;
+            if (b.pos < nt) {
+                const float4 q = ldg4(tpts + b.pos);
+                const float4 nq = ldg4(tnrm + b.pos);
+                const float4 n0 = ldg4(snrm + i);
+                const float3 np = rotate_rn(sT, n0.x, n0.y, n0.z);
+                v[33] = __fsqrt_rn(b.d2);
+                v[34] = b.d2;
+                if (b.d2 <= lp.max_pair_d2) {
+                    const float nx = np.x + nq.x, ny = np.y + nq.y, nz = np.z + nq.z;
+                    const float ppx = p.x - sO[0], ppy = p.y - sO[1], ppz = p.z - sO[2];
+                    const float qqx = q.x - sO[0], qqy = q.y - sO[1], qqz = q.z - sO[2];
+                    const float sx = ppx + qqx, sy = ppy + qqy, sz = ppz + qqz;
+                    const float dx = p.x - q.x, dy = p.y - q.y, dz = p.z - q.z;
+                    const float mx = sy * nz - sz * ny, my = sz * nx - sx * nz, mz = sx * ny - sy * nx;
+                    const float r = dx * nx + dy * ny + dz * nz;
+                    v[0] = mx * mx; v[1] = mx * my; v[2] = mx * mz; v[3] = my * my; v[4] = my * mz; v[5] = mz * mz;
+                    v[6] = mx * nx; v[7] = mx * ny; v[8] = mx * nz;
+                    v[9] = my * nx; v[10] = my * ny; v[11] = my * nz;
+                    v[12] = mz * nx; v[13] = mz * ny; v[14] = mz * nz;
+                    v[15] = nx * nx; v[16] = nx * ny; v[17] = nx * nz; v[18] = ny * ny; v[19] = ny * nz; v[20] = nz * nz;
+                    v[21] = mx * r; v[22] = my * r; v[23] = mz * r;
+                    v[24] = nx * r; v[25] = ny * r; v[26] = nz * r;
+                    v[27] = ppx; v[28] = ppy; v[29] = ppz;
+                    v[30] = qqx; v[31] = qqy; v[32] = qqz;
+                    v[35] = r * r;
+                    v[36] = 1.f;
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < ICP_NSUMS; k++) {
+            float x = v[k];
+            x += __shfl_xor_sync(0xffffffffu, x, 16);
+            x += __shfl_xor_sync(0xffffffffu, x, 8);
+            x += __shfl_xor_sync(0xffffffffu, x, 4);
+            x += __shfl_xor_sync(0xffffffffu, x, 2);
+            x += __shfl_xor_sync(0xffffffffu, x, 1);
+            if (lane == 0) wacc[warp][k] += (double)x;
+        }
+    }
+    __syncthreads();
+    if (tid < ICP_NSUMS) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < kNNWarps; w++) s += wacc[w][tid];
+        P.partial[((size_t)seg * P.blocks_per_seg + blk) * ICP_PART_STRIDE + tid] = s;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2: reduce + decide + solve + compose
+// ------------------------------------------------------------------------------------------------
+__device__ void mat34_mul(const double* A, const double* B, double* C) {  // C = A*B as 4x4 affine, 3x4 storage
+    double R[12];
+    for (int r = 0; r < 3; r++) {
+        for (int c = 0; c < 4; c++) {
+            double s = A[4 * r] * B[c] + A[4 * r + 1] * B[4 + c] + A[4 * r + 2] * B[8 + c];
+            if (c == 3) s += A[4 * r + 3];
+            R[4 * r + c] = s;
+        }
+    }
+    for (int i = 0; i < 12; i++) C[i] = R[i];
+}
+
+// Re-centre the raw sums (taken about `origin`) to the pair centroids, solve, compose.
+// Tinc: 3x4 row-major.  Returns 1 when a pivot was dropped.
+__device__ int solve_compose_dev(const double* S, const double* origin, double* Tinc, double* x, double* ratio_out) {
+    for (int i = 0; i < 12; i++) Tinc[i] = (i % 5 == 0) ? 1.0 : 0.0;
+    for (int i = 0; i < 6; i++) x[i] = 0.0;
+    *ratio_out = 0.0;
+    const double cnt = S[36];
+    if (cnt < 1.0) return 1;
+    const double A[9] = {S[0], S[1], S[2], S[1], S[3], S[4], S[2], S[4], S[5]};
+    double B[9];
+    for (int i = 0; i < 9; i++) B[i] = S[6 + i];
+    const double C[9] = {S[15], S[16], S[17], S[16], S[18], S[19], S[17], S[19], S[20]};
+    double dp[3], dq[3], de[3], ep[3];
+    for (int k = 0; k < 3; k++) {
+        dp[k] = S[27 + k] / cnt;
+        dq[k] = S[30 + k] / cnt;
+        de[k] = dp[k] + dq[k];
+        ep[k] = dp[k] - dq[k];
+    }
+    // m = m' - K n with K = skew(de);  r = r' - ep.n
+    const double K[9] = {0, -de[2], de[1], de[2], 0, -de[0], -de[1], de[0], 0};
+    double BKt[9], KC[9], KCKt[9];
+    for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 3; c++) {
+            double s1 = 0, s2 = 0;
+            for (int k = 0; k < 3; k++) { s1 += B[3 * r + k] * K[3 * c + k]; s2 += K[3 * r + k] * C[3 * k + c]; }
+            BKt[3 * r + c] = s1;
+            KC[3 * r + c] = s2;
+        }
+    for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 3; c++) {
+            double s = 0;
+            for (int k = 0; k < 3; k++) s += KC[3 * r + k] * K[3 * c + k];
+            KCKt[3 * r + c] = s;
+        }
+    double H[36];
+    for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 3; c++) {
+            double at = A[3 * r + c] - BKt[3 * r + c] - BKt[3 * c + r] + KCKt[3 * r + c];
+            double bt = B[3 * r + c] - KC[3 * r + c];
+            H[6 * r + c] = at;
+            H[6 * r + 3 + c] = bt;
+            H[6 * (3 + c) + r] = bt;
+            H[6 * (3 + r) + 3 + c] = C[3 * r + c];
+        }
+    double Ce[3], Be[3];
+    for (int r = 0; r < 3; r++) {
+        Ce[r] = C[3 * r] * ep[0] + C[3 * r + 1] * ep[1] + C[3 * r + 2] * ep[2];
+        Be[r] = B[3 * r] * ep[0] + B[3 * r + 1] * ep[1] + B[3 * r + 2] * ep[2];
+    }
+    const double bn[3] = {S[24], S[25], S[26]};
+    const double Kbn[3] = {de[1] * bn[2] - de[2] * bn[1], de[2] * bn[0] - de[0] * bn[2], de[0] * bn[1] - de[1] * bn[0]};
+    const double KCe[3] = {de[1] * Ce[2] - de[2] * Ce[1], de[2] * Ce[0] - de[0] * Ce[2], de[0] * Ce[1] - de[1] * Ce[0]};
+    double g[6];
+    for (int r = 0; r < 3; r++) {
+        g[r] = S[21 + r] - Be[r] - Kbn[r] + KCe[r];
+        g[3 + r] = bn[r] - Ce[r];
+    }
+    // LDL^T with relative pivot guard: d_j <= 1e-6 * H_jj drops component j
+    double L[36], D[6];
+    int dead[6];
+    for (int i = 0; i < 36; i++) L[i] = 0.0;
+    int degenerate = 0;
+    double minratio = 1.0;
+    for (int j = 0; j < 6; j++) {
+        double d = H[6 * j + j];
+        for (int k = 0; k < j; k++)
+            if (!dead[k]) d -= L[6 * j + k] * L[6 * j + k] * D[k];
+        double ratio = H[6 * j + j] > 0 ? d / H[6 * j + j] : 0.0;
+        if (ratio < minratio) minratio = ratio;
+        dead[j] = 0;
+        if (!(d > 1e-6 * H[6 * j + j]) || !(H[6 * j + j] > 0)) { dead[j] = 1; degenerate = 1; D[j] = 0; continue; }
+        D[j] = d;
+        for (int i = j + 1; i < 6; i++) {
+            double vv = H[6 * i + j];
+            for (int k = 0; k < j; k++)
+                if (!dead[k]) vv -= L[6 * i + k] * L[6 * j + k] * D[k];
+            L[6 * i + j] = vv / d;
+        }
+    }
+    *ratio_out = minratio;
+    double y[6];
+    for (int i = 0; i < 6; i++) {
+        double vv = -g[i];
+        for (int k = 0; k < i; k++)
+            if (!dead[k]) vv -= L[6 * i + k] * y[k];
+        y[i] = dead[i] ? 0.0 : vv;
+    }
+    for (int i = 0; i < 6; i++) y[i] = dead[i] ? 0.0 : y[i] / D[i];
+    for (int i = 5; i >= 0; i--) {
+        if (dead[i]) { x[i] = 0.0; continue; }
+        double vv = y[i];
+        for (int k = i + 1; k < 6; k++)
+            if (!dead[k]) vv -= L[6 * k + i] * x[k];
+        x[i] = vv;
+    }
+    // Tinc = Tr(qbar) R Tr(t cos th) R Tr(-pbar):  x -> R(R(x - pbar) + t cos th) + qbar
+    const double an = sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
+    const double th = atan(an);
+    double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    if (an > 1e-300) {
+        const double u[3] = {x[0] / an, x[1] / an, x[2] / an};
+        const double c = cos(th), s = sin(th), Cc = 1.0 - c;
+        R[0] = c + u[0] * u[0] * Cc;        R[1] = u[0] * u[1] * Cc - u[2] * s; R[2] = u[0] * u[2] * Cc + u[1] * s;
+        R[3] = u[1] * u[0] * Cc + u[2] * s; R[4] = c + u[1] * u[1] * Cc;        R[5] = u[1] * u[2] * Cc - u[0] * s;
+        R[6] = u[2] * u[0] * Cc - u[1] * s; R[7] = u[2] * u[1] * Cc + u[0] * s; R[8] = c + u[2] * u[2] * Cc;
+    }
+    const double ct = cos(th);
+    double pbar[3], qbar[3], tc[3];
+    for (int k = 0; k < 3; k++) { pbar[k] = origin[k] + dp[k]; qbar[k] = origin[k] + dq[k]; tc[k] = x[3 + k] * ct; }
+    double R2[9];
+    for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 3; c++) R2[3 * r + c] = R[3 * r] * R[c] + R[3 * r + 1] * R[3 + c] + R[3 * r + 2] * R[6 + c];
+    for (int r = 0; r < 3; r++) {
+        Tinc[4 * r] = R2[3 * r]; Tinc[4 * r + 1] = R2[3 * r + 1]; Tinc[4 * r + 2] = R2[3 * r + 2];
+        Tinc[4 * r + 3] = qbar[r] + (R[3 * r] * tc[0] + R[3 * r + 1] * tc[1] + R[3 * r + 2] * tc[2]) -
+                          (R2[3 * r] * pbar[0] + R2[3 * r + 1] * pbar[1] + R2[3 * r + 2] * pbar[2]);
+    }
+    return degenerate;
+}
+
+__global__ void __launch_bounds__(kSolveThreads) solve_kernel(const __grid_constant__ SolveParams P) {
+    const uint32_t seg = blockIdx.x;
+    SegState* st = P.state + seg;
+    __shared__ double sPart[kSolveParts][ICP_NSUMS];
+    __shared__ double sS[ICP_NSUMS];
+    const int tid = threadIdx.x;
+    if (st->done) return;
+    if (P.mode != 2) {
+        const int v = tid % ICP_NSUMS, part = tid / ICP_NSUMS;
+        if (part < kSolveParts) {
+            double s = 0.0;
+            const double* row = P.partial + (size_t)seg * P.blocks_per_seg * ICP_PART_STRIDE + v;
+            for (uint32_t b = part; b < P.blocks_per_seg; b += kSolveParts) s += row[(size_t)b * ICP_PART_STRIDE];
+            sPart[part][v] = s;
+        }
+        __syncthreads();
+        if (tid < ICP_NSUMS) {
+            double s = 0.0;
+            for (int p = 0; p < kSolveParts; p++) s += sPart[p][tid];
+            sS[tid] = s;
+            if (P.mode == 1 || P.mode == 3) P.gsum[(size_t)seg * ICP_PART_STRIDE + tid] = s;
+        }
+        __syncthreads();
+        if (P.mode == 1) return;
+    } else {
+        if (tid < ICP_NSUMS) sS[tid] = P.gsum[(size_t)seg * ICP_PART_STRIDE + tid];
+        __syncthreads();
+    }
+    if (tid != 0) return;
+
+    const LoopParams lp = *P.lp;
+    const double diff = sS[33];
+    const int k = st->searches;
+    st->searches = k + 1;
+    st->diff = diff;
+    st->sumd2 = sS[34];
+    if (lp.trace && P.trace_T && k < P.trace_stride) {
+        float* tt = P.trace_T + ((size_t)seg * P.trace_stride + k) * 12;
+        for (int i = 0; i < 12; i++) tt[i] = st->Tf[i];
+        P.trace_diff[(size_t)seg * P.trace_stride + k] = diff;
+    }
+    if (P.mode == 3) { st->done = 1; return; }
+    if (!(diff > (double)lp.diff_threshold)) { st->done = 1; st->converged = 1; return; }      // myicp.cpp:123
+    if (st->iter >= lp.max_iters) { st->done = 1; st->converged = 0; return; }                 // iters++ < max_iters
+    if (lp.rel_diff_tol > 0.0 && k > 0 && fabs(st->prev_diff - diff) <= lp.rel_diff_tol * st->prev_diff) {
+        st->done = 1; st->converged = 2; return;
+    }
+    st->prev_diff = diff;
+    double Tinc[12], x[6], ratio;
+    const double origin[3] = {st->origin[0], st->origin[1], st->origin[2]};
+    const int deg = solve_compose_dev(sS, origin, Tinc, x, &ratio);
+    if (deg) st->degenerate = 1;
+    if (ratio < st->min_ratio) st->min_ratio = ratio;
+    double Tn[12];
+    mat34_mul(Tinc, st->T, Tn);                                                                // myicp.cpp:138
+    for (int i = 0; i < 12; i++) { st->T[i] = Tn[i]; st->Tf[i] = (float)Tn[i]; }
+    st->iter = st->iter + 1;
+    st->pairs = (unsigned long long)(sS[36] + 0.5);
+}
+
+__global__ void solve_compose_kernel(const double* in /*37 sums + 3 origin*/, double* out /*12 T + 6 x + ratio + deg*/) {
+    double Tinc[12], x[6], ratio;
+    int deg = solve_compose_dev(in, in + ICP_NSUMS, Tinc, x, &ratio);
+    for (int i = 0; i < 12; i++) out[i] = Tinc[i];
+    for (int i = 0; i < 6; i++) out[12 + i] = x[i];
+    out[18] = ratio;
+    out[19] = (double)deg;
+}
+
+// ------------------------------------------------------------------------------------------------
+// exports
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) export_corr_kernel(CloudView src, CloudView tgt, const SegState* __restrict__ state,
+                                                          const uint32_t* __restrict__ corr, uint32_t src_max_count,
+                                                          int32_t* __restrict__ idx_out, float* __restrict__ d2_out) {
+    size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t pitch = src.shape.pitch;
+    if (j >= (size_t)src.nseg * pitch) return;
+    uint32_t seg = (uint32_t)(j / pitch), i = (uint32_t)(j - (size_t)seg * pitch);
+    if (i >= src.counts[seg]) return;
+    float4 s = src.pts[j];
+    uint32_t pos = corr[j];
+    size_t o = (size_t)seg * src_max_count + __float_as_uint(s.w);
+    if (pos < tgt.counts[seg]) {
+        float4 t = tgt.pts[(size_t)seg * tgt.shape.pitch + pos];
+        float3 p = apply_rn(state[seg].Tf, s.x, s.y, s.z);
+        idx_out[o] = (int32_t)__float_as_uint(t.w);
+        d2_out[o] = dist2_rn(p.x, p.y, p.z, t.x, t.y, t.z);
+    } else {
+        idx_out[o] = -1;
+        d2_out[o] = __int_as_float(0x7f800000);
+    }
+}
+
+struct T12 { float m[12]; };
+
+__global__ void __launch_bounds__(256) export_transformed_kernel(CloudView src, T12 T, uint32_t src_max_count,
+                                                                 float* __restrict__ out, uint32_t out_stride_floats) {
+    size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t pitch = src.shape.pitch;
+    if (j >= (size_t)src.nseg * pitch) return;
+    uint32_t seg = (uint32_t)(j / pitch), i = (uint32_t)(j - (size_t)seg * pitch);
+    if (i >= src.counts[seg]) return;
+    float4 s = src.pts[j];
+    float3 p = apply_rn(T.m, s.x, s.y, s.z);
+    float* o = out + ((size_t)seg * src_max_count + __float_as_uint(s.w)) * out_stride_floats;
+    o[0] = p.x; o[1] = p.y; o[2] = p.z;
+}
+
+bool stream_capturable(cudaStream_t s) {
+    return s != nullptr && s != cudaStreamLegacy && s != cudaStreamPerThread;
+}
+
+}  // namespace
+
+static int ensure_io(icpsymm_ctx* ctx, size_t bytes) {
+    char* p = (char*)ctx->io_buf;
+    int rc = icp_reserve(ctx, &p, &ctx->io_bytes, bytes);
+    ctx->io_buf = p;
+    return rc;
+}
+
+static uint32_t choose_blocks_per_seg(const icpsymm_ctx* ctx, uint32_t nseg, uint32_t max_queries) {
+    uint32_t ntiles = (max_queries + kNNThreads - 1) / kNNThreads;
+    if (ntiles < 1) ntiles = 1;
+    uint32_t bps;
+    if (ctx->opt_grid_blocks > 0) bps = (uint32_t)ctx->opt_grid_blocks;
+    else {
+        uint32_t target = (uint32_t)ctx->sm_count * 8u;
+        bps = (target + nseg - 1) / nseg;
+    }
+    if (bps > ntiles) bps = ntiles;
+    if (bps < 1) bps = 1;
+    return bps;
+}
+
+static void launch_iteration(icpsymm_ctx* ctx, const NNParams& np, SolveParams sp, uint32_t nseg, bool use_comm,
+                             cudaEvent_t* ev /*4 events or null*/) {
+    cudaStream_t st = ctx->stream;
+    if (ev) cudaEventRecord(ev[0], st);
+    nn_accum_kernel<<<nseg * np.blocks_per_seg, kNNThreads, 0, st>>>(np);
+    if (ev) { cudaEventRecord(ev[1], st); cudaEventRecord(ev[2], st); }
+    if (!use_comm) {
+        solve_kernel<<<nseg, kSolveThreads, 0, st>>>(sp);
+    } else {
+        sp.mode = 1;
+        solve_kernel<<<nseg, kSolveThreads, 0, st>>>(sp);
+        icp_comm_allreduce(ctx, sp.gsum, (size_t)nseg * ICP_PART_STRIDE);
+        sp.mode = 2;
+        solve_kernel<<<nseg, kSolveThreads, 0, st>>>(sp);
+    }
+    if (ev) cudaEventRecord(ev[3], st);
+}
+
+int icp_run_loop(icpsymm_ctx* ctx, int max_iters, float thr, const float* T_init, const double* origin,
+                 bool single_search, float* T_out, icpsymm_stats* stats) {
+    CloudSet& S = ctx->src;
+    CloudSet& T = ctx->tgt;
+    if (!S.valid || !T.valid) return icp_fail_msg(ctx, ICPSYMM_ERR_NOT_READY, "set_source / set_target first");
+    if (S.nseg != T.nseg) return icp_fail_msg(ctx, ICPSYMM_ERR_SIZE, "source and target hold a different number of pairs");
+    if (!single_search && (!S.has_normals || !T.has_normals))
+        return icp_fail_msg(ctx, ICPSYMM_ERR_NOT_READY, "normals missing: call icpsymm_estimate_normals or icpsymm_set_normals");
+    if (max_iters < 0) return icp_fail_msg(ctx, ICPSYMM_ERR_INVALID, "max_iters < 0");
+    if (ctx->opt_identity)
+        for (uint32_t s = 0; s < S.nseg; s++)
+            if (S.h_counts[s] != T.h_counts[s])
+                return icp_fail_msg(ctx, ICPSYMM_ERR_SIZE, "identity pairing needs equal cloud sizes (func.cpp:21)");
+    const uint32_t nseg = S.nseg;
+    cudaStream_t st = ctx->stream;
+    int rc;
+
+    uint32_t max_q = S.max_count;
+    if (ctx->shard_world > 1) max_q = (uint32_t)((S.max_count + ctx->shard_world - 1) / ctx->shard_world) + 1;
+    const uint32_t bps = choose_blocks_per_seg(ctx, nseg, max_q);
+    ctx->last_blocks_per_seg = bps;
+
+    if ((rc = icp_reserve(ctx, &ctx->d_state, &ctx->state_cap, nseg))) return rc;
+    if (ctx->h_state_cap < nseg) {
+        if (ctx->h_state) ICP_CUDA_CHECK(cudaFreeHost(ctx->h_state));
+        ctx->h_state = nullptr;
+        ICP_CUDA_CHECK(cudaMallocHost((void**)&ctx->h_state, sizeof(SegState) * nseg));
+        ctx->h_state_cap = nseg;
+    }
+    if ((rc = icp_reserve(ctx, &ctx->partial, &ctx->partial_cap, (size_t)nseg * bps * ICP_PART_STRIDE))) return rc;
+    if ((rc = icp_reserve(ctx, &ctx->gsum, &ctx->gsum_cap, (size_t)nseg * ICP_PART_STRIDE))) return rc;
+    if ((rc = icp_reserve(ctx, &ctx->corr_pos, &ctx->corr_cap, (size_t)nseg * S.shape.pitch))) return rc;
+    if (!ctx->d_lp) ICP_CUDA_CHECK(cudaMalloc((void**)&ctx->d_lp, sizeof(LoopParams)));
+    const int n_search = single_search ? 1 : max_iters + 1;
+    if (ctx->opt_trace) {
+        size_t need = (size_t)nseg * n_search;
+        size_t c1 = ctx->trace_cap, c2 = ctx->trace_cap;
+        if ((rc = icp_reserve(ctx, &ctx->trace_T, &c1, need * 12))) return rc;
+        if ((rc = icp_reserve(ctx, &ctx->trace_diff, &c2, need))) return rc;
+        ctx->trace_cap = c2 < c1 / 12 ? c2 : c1 / 12;
+        ctx->trace_stride = n_search;
+    }
+
+    LoopParams lp;
+    lp.max_iters = max_iters;
+    lp.diff_threshold = thr;
+    lp.rel_diff_tol = ctx->opt_rel_diff_tol;
+    lp.max_pair_d2 = ctx->opt_max_pair_dist > 0.f ? ctx->opt_max_pair_dist * ctx->opt_max_pair_dist : INFINITY;
+    lp.identity_pairs = ctx->opt_identity;
+    lp.warm_start = ctx->opt_warm_start;
+    lp.trace = ctx->opt_trace;
+    set_lp_kernel<<<1, 1, 0, st>>>(ctx->d_lp, lp);
+
+    InitArgs ia;
+    memset(&ia, 0, sizeof ia);
+    if (T_init) {
+        ia.has_T = 1;
+        for (int i = 0; i < 12; i++) ia.T[i] = T_init[i];
+    }
+    if (origin) {
+        ia.has_origin = 1;
+        for (int i = 0; i < 3; i++) ia.origin[i] = origin[i];
+    }
+    init_state_kernel<<<(nseg + 127) / 128, 128, 0, st>>>(ctx->d_state, nseg, ia, T.bb_lo, T.bb_hi);
+    ICP_CUDA_CHECK(cudaMemsetAsync(ctx->corr_pos, 0xff, sizeof(uint32_t) * (size_t)nseg * S.shape.pitch, st));
+
+    NNParams np;
+    np.src = S.view(); np.tgt = T.view();
+    np.state = ctx->d_state; np.lp = ctx->d_lp; np.corr_pos = ctx->corr_pos; np.partial = ctx->partial;
+    np.blocks_per_seg = bps; np.shard_rank = ctx->shard_rank; np.shard_world = ctx->shard_world;
+    SolveParams sp;
+    sp.state = ctx->d_state; sp.lp = ctx->d_lp; sp.partial = ctx->partial; sp.gsum = ctx->gsum;
+    sp.src_counts = S.counts; sp.trace_T = ctx->opt_trace ? ctx->trace_T : nullptr;
+    sp.trace_diff = ctx->opt_trace ? ctx->trace_diff : nullptr;
+    sp.blocks_per_seg = bps; sp.trace_stride = ctx->trace_stride; sp.mode = single_search ? 3 : 0;
+
+    const bool use_comm = ctx->nccl_comm != nullptr && ctx->shard_world > 1;
+    const bool timing = ctx->opt_kernel_timing != 0;
+    const bool use_graph = ctx->opt_use_graph && !timing && !single_search && !use_comm && stream_capturable(st);
+
+    if (!ctx->ev_begin) {
+        ICP_CUDA_CHECK(cudaEventCreate(&ctx->ev_begin));
+        ICP_CUDA_CHECK(cudaEventCreate(&ctx->ev_end));
+    }
+    if (timing && ctx->ev_pool_n < 4 * n_search) {
+        for (int i = 0; i < ctx->ev_pool_n; i++) cudaEventDestroy(ctx->ev_pool[i]);
+        free(ctx->ev_pool);
+        ctx->ev_pool_n = 4 * n_search;
+        ctx->ev_pool = (cudaEvent_t*)malloc(sizeof(cudaEvent_t) * ctx->ev_pool_n);
+        for (int i = 0; i < ctx->ev_pool_n; i++) ICP_CUDA_CHECK(cudaEventCreate(&ctx->ev_pool[i]));
+    }
+
+    if (use_graph) {
+        GraphKey key;
+        key.max_iters = max_iters; key.nseg = nseg; key.blocks_per_seg = bps;
+        key.src_pitch = S.shape.pitch; key.tgt_pitch = T.shape.pitch;
+        key.p0 = S.pts; key.p1 = T.pts; key.p2 = ctx->partial; key.p3 = ctx->corr_pos; key.p4 = ctx->d_state;
+        key.p5 = ctx->opt_trace ? (const void*)ctx->trace_T : (const void*)T.boxes;
+        key.shard_rank = ctx->shard_rank; key.shard_world = ctx->shard_world; key.trace = ctx->opt_trace;
+        // pointers of the remaining arrays change only together with the ones above (same reserve calls)
+        if (!ctx->graph_exec || !(ctx->graph_key == key)) {
+            if (ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }
+            cudaGraph_t g = nullptr;
+            ICP_CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+            for (int k = 0; k < n_search; k++) launch_iteration(ctx, np, sp, nseg, false, nullptr);
+            ICP_CUDA_CHECK(cudaStreamEndCapture(st, &g));
+            ICP_CUDA_CHECK(cudaGraphInstantiate(&ctx->graph_exec, g, 0));
+            cudaGraphDestroy(g);
+            ctx->graph_key = key;
+        }
+        ICP_CUDA_CHECK(cudaEventRecord(ctx->ev_begin, st));
+        ICP_CUDA_CHECK(cudaGraphLaunch(ctx->graph_exec, st));
+        ICP_CUDA_CHECK(cudaEventRecord(ctx->ev_end, st));
+    } else {
+        ICP_CUDA_CHECK(cudaEventRecord(ctx->ev_begin, st));
+        for (int k = 0; k < n_search; k++)
+            launch_iteration(ctx, np, sp, nseg, use_comm, timing ? ctx->ev_pool + 4 * k : nullptr);
+        ICP_CUDA_CHECK(cudaEventRecord(ctx->ev_end, st));
+    }
+    ICP_CUDA_CHECK(cudaGetLastError());
+    ICP_CUDA_CHECK(cudaMemcpyAsync(ctx->h_state, ctx->d_state, sizeof(SegState) * nseg, cudaMemcpyDeviceToHost, st));
+    ICP_CUDA_CHECK(cudaStreamSynchronize(st));
+    ctx->have_corr = true;
+
+    float loop_ms = 0.f;
+    cudaEventElapsedTime(&loop_ms, ctx->ev_begin, ctx->ev_end);
+    int max_searches = 0;
+    for (uint32_t s = 0; s < nseg; s++) max_searches = ctx->h_state[s].searches > max_searches ? ctx->h_state[s].searches : max_searches;
+    float search_ms = 0.f, solve_ms = 0.f;
+    int search_launches = 0, solve_launches = 0;
+    if (timing) {
+        for (int k = 0; k < max_searches && k < n_search; k++) {
+            float a = 0.f, b = 0.f;
+            cudaEventElapsedTime(&a, ctx->ev_pool[4 * k], ctx->ev_pool[4 * k + 1]);
+            cudaEventElapsedTime(&b, ctx->ev_pool[4 * k + 2], ctx->ev_pool[4 * k + 3]);
+            search_ms += a; solve_ms += b;
+            search_launches++; solve_launches++;
+        }
+    }
+    int any_deg = 0;
+    for (uint32_t s = 0; s < nseg; s++) {
+        const SegState& hs = ctx->h_state[s];
+        if (T_out) {
+            float* o = T_out + 16 * (size_t)s;
+            for (int i = 0; i < 12; i++) o[i] = hs.Tf[i];
+            o[12] = o[13] = o[14] = 0.f; o[15] = 1.f;
+        }
+        if (hs.degenerate) any_deg = 1;
+        if (stats) {
+            icpsymm_stats& o = stats[s];
+            memset(&o, 0, sizeof o);
+            o.iters = hs.iter; o.converged = hs.converged; o.degenerate = hs.degenerate; o.searches = hs.searches;
+            o.diff = hs.diff;
+            uint32_t nq = S.h_counts[s];
+            if (ctx->shard_world > 1) {
+                uint32_t lo = (uint32_t)(((unsigned long long)nq * ctx->shard_rank) / ctx->shard_world);
+                uint32_t hi = (uint32_t)(((unsigned long long)nq * (ctx->shard_rank + 1)) / ctx->shard_world);
+                nq = use_comm ? nq : hi - lo;
+            }
+            o.rmse = nq ? sqrt(hs.sumd2 / (double)nq) : 0.0;
+            o.min_pivot_ratio = hs.min_ratio; o.pairs = hs.pairs;
+            o.loop_ms = loop_ms; o.search_ms = search_ms; o.solve_ms = solve_ms;
+            o.search_launches = search_launches; o.solve_launches = solve_launches;
+        }
+    }
+    return any_deg ? ICPSYMM_WARN_DEGENERATE : ICPSYMM_OK;
+}
+
+int icp_run_single(icpsymm_ctx* ctx, const float* T16, const double* origin, icpsymm_stats* stats) {
+    float T12v[12];
+    if (T16) for (int i = 0; i < 12; i++) T12v[i] = T16[i];
+    return icp_run_loop(ctx, 0, 0.f, T16 ? T12v : nullptr, origin, true, nullptr, stats);
+}
+
+int icp_export_correspondences(icpsymm_ctx* ctx, int32_t* idx_out, float* d2_out) {
+    CloudSet& S = ctx->src;
+    if (!ctx->have_corr || !S.valid || !ctx->tgt.valid) return icp_fail_msg(ctx, ICPSYMM_ERR_NOT_READY, "no search has run");
+    size_t n = (size_t)S.nseg * S.max_count;
+    int rc = ensure_io(ctx, n * 8);
+    if (rc) return rc;
+    int32_t* d_idx = (int32_t*)ctx->io_buf;
+    float* d_d2 = (float*)((char*)ctx->io_buf + n * 4);
+    cudaStream_t st = ctx->stream;
+    ICP_CUDA_CHECK(cudaMemsetAsync(d_idx, 0xff, n * 4, st));
+    ICP_CUDA_CHECK(cudaMemsetAsync(d_d2, 0, n * 4, st));
+    size_t slots = (size_t)S.nseg * S.shape.pitch;
+    export_corr_kernel<<<(uint32_t)((slots + 255) / 256), 256, 0, st>>>(S.view(), ctx->tgt.view(), ctx->d_state,
+                                                                         ctx->corr_pos, S.max_count, d_idx, d_d2);
+    ICP_CUDA_CHECK(cudaGetLastError());
+    if (idx_out) ICP_CUDA_CHECK(cudaMemcpyAsync(idx_out, d_idx, n * 4, cudaMemcpyDeviceToHost, st));
+    if (d2_out) ICP_CUDA_CHECK(cudaMemcpyAsync(d2_out, d_d2, n * 4, cudaMemcpyDeviceToHost, st));
+    ICP_CUDA_CHECK(cudaStreamSynchronize(st));
+    return ICPSYMM_OK;
+}
+
+int icp_export_transformed(icpsymm_ctx* ctx, const float* T, float* xyz_out, size_t stride_bytes) {
+    CloudSet& S = ctx->src;
+    if (!S.valid) return icp_fail_msg(ctx, ICPSYMM_ERR_NOT_READY, "set_source first");
+    if (!T || !xyz_out || stride_bytes < 12 || (stride_bytes & 3)) return icp_fail_msg(ctx, ICPSYMM_ERR_INVALID, "bad argument");
+    size_t n = (size_t)S.nseg * S.max_count;
+    int rc = ensure_io(ctx, n * stride_bytes);
+    if (rc) return rc;
+    cudaStream_t st = ctx->stream;
+    ICP_CUDA_CHECK(cudaMemsetAsync(ctx->io_buf, 0, n * stride_bytes, st));
+    T12 t;
+    for (int i = 0; i < 12; i++) t.m[i] = T[i];
+    size_t slots = (size_t)S.nseg * S.shape.pitch;
+    export_transformed_kernel<<<(uint32_t)((slots + 255) / 256), 256, 0, st>>>(S.view(), t, S.max_count,
+                                                                                (float*)ctx->io_buf,
+                                                                                (uint32_t)(stride_bytes / 4));
+    ICP_CUDA_CHECK(cudaGetLastError());
+    ICP_CUDA_CHECK(cudaMemcpyAsync(xyz_out, ctx->io_buf, n * stride_bytes, cudaMemcpyDeviceToHost, st));
+    ICP_CUDA_CHECK(cudaStreamSynchronize(st));
+    return ICPSYMM_OK;
+}
+
+int icp_read_sums(icpsymm_ctx* ctx, double* sums, double* origin_out) {
+    double tmp[ICP_PART_STRIDE];
+    ICP_CUDA_CHECK(cudaMemcpyAsync(tmp, ctx->gsum, sizeof(double) * ICP_PART_STRIDE, cudaMemcpyDeviceToHost, ctx->stream));
+    ICP_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < ICP_NSUMS; i++) sums[i] = tmp[i];
+    if (origin_out) for (int i = 0; i < 3; i++) origin_out[i] = ctx->h_state[0].origin[i];
+    return ICPSYMM_OK;
+}
+
+int icp_solve_compose_device(icpsymm_ctx* ctx, const double* sums, const double* origin, double* Tinc, double* x,
+                             double* ratio) {
+    int rc = ensure_io(ctx, sizeof(double) * 64);
+    if (rc) return rc;
+    double in[ICP_NSUMS + 3], out[20];
+    for (int i = 0; i < ICP_NSUMS; i++) in[i] = sums[i];
+    for (int i = 0; i < 3; i++) in[ICP_NSUMS + i] = origin ? origin[i] : 0.0;
+    double* d_in = (double*)ctx->io_buf;
+    double* d_out = d_in + 40;
+    cudaStream_t st = ctx->stream;
+    ICP_CUDA_CHECK(cudaMemcpyAsync(d_in, in, sizeof in, cudaMemcpyHostToDevice, st));
+    solve_compose_kernel<<<1, 1, 0, st>>>(d_in, d_out);
+    ICP_CUDA_CHECK(cudaGetLastError());
+    ICP_CUDA_CHECK(cudaMemcpyAsync(out, d_out, sizeof out, cudaMemcpyDeviceToHost, st));
+    ICP_CUDA_CHECK(cudaStreamSynchronize(st));
+    if (Tinc) {
+        for (int i = 0; i < 12; i++) Tinc[i] = out[i];
+        Tinc[12] = Tinc[13] = Tinc[14] = 0.0; Tinc[15] = 1.0;
+    }
+    if (x) for (int i = 0; i < 6; i++) x[i] = out[12 + i];
+    if (ratio) *ratio = out[18];
+    return out[19] != 0.0 ? ICPSYMM_WARN_DEGENERATE : ICPSYMM_OK;
+}

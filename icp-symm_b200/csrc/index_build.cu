@@ -1,0 +1,319 @@
+// index_build.cu -- upload, Morton sort and implicit box hierarchy of a cloud set.
+//
+// Replaces pasteInMatrix (ICP/func.cpp:5-15: AoS cloud -> dense matrices) and the kd-tree
+// construction hidden inside pcl::search::KdTree (ICP/myicp.cpp:158-159).  One-off per cloud;
+// the hot loop only reads the result.  Steps, all on the context stream:
+//   bbox reduce -> 30-bit Morton key per point (uniform cell size) -> radix sort (CUB, keys are
+//   segment<<32 | morton so a whole batch sorts in one pass) -> gather into the float4 layout
+//   with the original index in .w -> tight leaf boxes -> one kernel per upper level.
+#include <cfloat>
+#include <cstring>
+#include <cub/device/device_radix_sort.cuh>
+
+#include "internal.h"
+
+namespace {
+
+constexpr uint32_t kPadKey = 0x40000000u;  // sorts after every 30-bit Morton code
+
+__global__ void bbox_init_kernel(uint32_t* bbox, uint32_t nseg, int* flags) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nseg * 8) bbox[i] = ((i & 7) < 4) ? 0xffffffffu : 0u;
+    if (i == 0) flags[0] = 0;
+}
+
+// grid: (blocks per segment, nseg)
+__global__ void __launch_bounds__(256) bbox_kernel(const char* __restrict__ raw, size_t stride_bytes,
+                                                   const uint32_t* __restrict__ counts, uint32_t max_count,
+                                                   uint32_t* __restrict__ bbox, int* __restrict__ flags) {
+    const uint32_t seg = blockIdx.y;
+    const uint32_t cnt = counts[seg];
+    uint32_t lo[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu}, hi[3] = {0u, 0u, 0u};
+    int bad = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) {
+        const float* p = reinterpret_cast<const float*>(raw + ((size_t)seg * max_count + i) * stride_bytes);
+        float v[3] = {p[0], p[1], p[2]};
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+            if (!isfinite(v[d])) bad = 1;
+            uint32_t o = float_to_ordered(v[d]);
+            lo[d] = min(lo[d], o);
+            hi[d] = max(hi[d], o);
+        }
+    }
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+        lo[d] = __reduce_min_sync(0xffffffffu, lo[d]);
+        hi[d] = __reduce_max_sync(0xffffffffu, hi[d]);
+    }
+    bad = __any_sync(0xffffffffu, bad);
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+            atomicMin(&bbox[seg * 8 + d], lo[d]);
+            atomicMax(&bbox[seg * 8 + 4 + d], hi[d]);
+        }
+        if (bad) atomicAdd(flags, 1);
+    }
+}
+
+__global__ void bbox_finish_kernel(const uint32_t* __restrict__ bbox, const uint32_t* __restrict__ counts,
+                                   float4* __restrict__ bb_lo, float4* __restrict__ bb_hi, uint32_t nseg) {
+    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nseg) return;
+    if (counts[s] == 0) {
+        bb_lo[s] = make_float4(0.f, 0.f, 0.f, 0.f);
+        bb_hi[s] = make_float4(0.f, 0.f, 0.f, 0.f);
+        return;
+    }
+    bb_lo[s] = make_float4(ordered_to_float(bbox[s * 8]), ordered_to_float(bbox[s * 8 + 1]),
+                           ordered_to_float(bbox[s * 8 + 2]), 0.f);
+    bb_hi[s] = make_float4(ordered_to_float(bbox[s * 8 + 4]), ordered_to_float(bbox[s * 8 + 5]),
+                           ordered_to_float(bbox[s * 8 + 6]), 0.f);
+}
+
+__device__ __forceinline__ uint32_t spread10(uint32_t v) {  // 10 bits -> every third bit
+    v &= 0x3ffu;
+    v = (v | (v << 16)) & 0x030000ffu;
+    v = (v | (v << 8)) & 0x0300f00fu;
+    v = (v | (v << 4)) & 0x030c30c3u;
+    v = (v | (v << 2)) & 0x09249249u;
+    return v;
+}
+
+// one thread per slot of the pitched layout
+__global__ void __launch_bounds__(256) morton_kernel(const char* __restrict__ raw, size_t stride_bytes,
+                                                     const uint32_t* __restrict__ counts, uint32_t max_count,
+                                                     uint32_t pitch, uint32_t nseg, const float4* __restrict__ bb_lo,
+                                                     const float4* __restrict__ bb_hi,
+                                                     unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals) {
+    size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= (size_t)nseg * pitch) return;
+    uint32_t seg = (uint32_t)(j / pitch), i = (uint32_t)(j - (size_t)seg * pitch);
+    uint32_t code = kPadKey;
+    if (i < counts[seg]) {
+        const float* p = reinterpret_cast<const float*>(raw + ((size_t)seg * max_count + i) * stride_bytes);
+        float4 lo = bb_lo[seg], hi = bb_hi[seg];
+        float ext = fmaxf(fmaxf(hi.x - lo.x, hi.y - lo.y), hi.z - lo.z);
+        float scale = ext > 0.f ? 1023.5f / ext : 0.f;
+        uint32_t cx = min(1023u, (uint32_t)((p[0] - lo.x) * scale));
+        uint32_t cy = min(1023u, (uint32_t)((p[1] - lo.y) * scale));
+        uint32_t cz = min(1023u, (uint32_t)((p[2] - lo.z) * scale));
+        code = spread10(cx) | (spread10(cy) << 1) | (spread10(cz) << 2);
+    }
+    keys[j] = ((unsigned long long)seg << 32) | code;
+    vals[j] = i;
+}
+
+__global__ void __launch_bounds__(256) gather_kernel(const char* __restrict__ raw, size_t stride_bytes,
+                                                     const uint32_t* __restrict__ counts, uint32_t max_count,
+                                                     uint32_t pitch, uint32_t nseg, const uint32_t* __restrict__ vals,
+                                                     float4* __restrict__ pts, uint32_t* __restrict__ pos_of_orig) {
+    size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= (size_t)nseg * pitch) return;
+    uint32_t seg = (uint32_t)(j / pitch);
+    uint32_t v = vals[j];
+    if (v < counts[seg]) {
+        const float* p = reinterpret_cast<const float*>(raw + ((size_t)seg * max_count + v) * stride_bytes);
+        pts[j] = make_float4(p[0], p[1], p[2], __uint_as_float(v));
+        pos_of_orig[(size_t)seg * pitch + v] = (uint32_t)(j - (size_t)seg * pitch);
+    } else {
+        pts[j] = make_float4(FLT_MAX, FLT_MAX, FLT_MAX, __uint_as_float((uint32_t)ICP_INVALID_ID));
+    }
+}
+
+__device__ __forceinline__ void box_empty(float4& lo, float4& hi) {
+    const float inf = __int_as_float(0x7f800000);
+    lo = make_float4(inf, inf, inf, 0.f);
+    hi = make_float4(-inf, -inf, -inf, 0.f);
+}
+
+// level 0: one thread per (padded) leaf group of every segment
+__global__ void __launch_bounds__(256) leaf_box_kernel(const float4* __restrict__ pts, Box* __restrict__ boxes,
+                                                       TreeShape sh, uint32_t nseg) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t n0 = sh.level_cnt[0];
+    if (t >= (size_t)nseg * n0) return;
+    uint32_t seg = (uint32_t)(t / n0), g = (uint32_t)(t - (size_t)seg * n0);
+    float4 lo, hi;
+    box_empty(lo, hi);
+    if ((size_t)g * ICP_LEAF < sh.pitch) {
+        const float4* lp = pts + (size_t)seg * sh.pitch + (size_t)g * ICP_LEAF;
+#pragma unroll
+        for (int j = 0; j < ICP_LEAF; j++) {
+            float4 c = lp[j];
+            if (__float_as_uint(c.w) != (uint32_t)ICP_INVALID_ID) {
+                lo.x = fminf(lo.x, c.x); lo.y = fminf(lo.y, c.y); lo.z = fminf(lo.z, c.z);
+                hi.x = fmaxf(hi.x, c.x); hi.y = fmaxf(hi.y, c.y); hi.z = fmaxf(hi.z, c.z);
+            }
+        }
+    }
+    Box b; b.lo = lo; b.hi = hi;
+    boxes[(size_t)seg * sh.nodes_per_seg + sh.level_off[0] + g] = b;
+}
+
+__global__ void __launch_bounds__(256) upper_box_kernel(Box* __restrict__ boxes, TreeShape sh, uint32_t nseg, int level) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t nl = sh.level_cnt[level];
+    if (t >= (size_t)nseg * nl) return;
+    uint32_t seg = (uint32_t)(t / nl), i = (uint32_t)(t - (size_t)seg * nl);
+    float4 lo, hi;
+    box_empty(lo, hi);
+    const Box* child = boxes + (size_t)seg * sh.nodes_per_seg + sh.level_off[level - 1];
+    uint32_t nc = sh.level_cnt[level - 1];
+#pragma unroll
+    for (int k = 0; k < ICP_FAN; k++) {
+        uint32_t c = i * ICP_FAN + k;
+        if (c < nc) {
+            float4 clo = child[c].lo, chi = child[c].hi;
+            lo.x = fminf(lo.x, clo.x); lo.y = fminf(lo.y, clo.y); lo.z = fminf(lo.z, clo.z);
+            hi.x = fmaxf(hi.x, chi.x); hi.y = fmaxf(hi.y, chi.y); hi.z = fmaxf(hi.z, chi.z);
+        }
+    }
+    Box b; b.lo = lo; b.hi = hi;
+    boxes[(size_t)seg * sh.nodes_per_seg + sh.level_off[level] + i] = b;
+}
+
+inline uint32_t round_up(uint32_t v, uint32_t m) { return (v + m - 1) / m * m; }
+
+}  // namespace
+
+template <typename T>
+int icp_reserve(icpsymm_ctx* ctx, T** p, size_t* cap, size_t need) {
+    if (need <= *cap && *p) return ICPSYMM_OK;
+    if (*p) { ICP_CUDA_CHECK(cudaFree(*p)); *p = nullptr; *cap = 0; }
+    size_t n = need ? need : 1;
+    ICP_CUDA_CHECK(cudaMalloc((void**)p, n * sizeof(T)));
+    *cap = n;
+    return ICPSYMM_OK;
+}
+template int icp_reserve<float4>(icpsymm_ctx*, float4**, size_t*, size_t);
+template int icp_reserve<Box>(icpsymm_ctx*, Box**, size_t*, size_t);
+template int icp_reserve<uint32_t>(icpsymm_ctx*, uint32_t**, size_t*, size_t);
+template int icp_reserve<unsigned long long>(icpsymm_ctx*, unsigned long long**, size_t*, size_t);
+template int icp_reserve<double>(icpsymm_ctx*, double**, size_t*, size_t);
+template int icp_reserve<float>(icpsymm_ctx*, float**, size_t*, size_t);
+template int icp_reserve<char>(icpsymm_ctx*, char**, size_t*, size_t);
+template int icp_reserve<SegState>(icpsymm_ctx*, SegState**, size_t*, size_t);
+
+TreeShape icp_make_shape(uint32_t max_count) {
+    TreeShape sh;
+    memset(&sh, 0, sizeof sh);
+    sh.pitch = round_up(max_count ? max_count : 1, ICP_LEAF);
+    uint32_t cnt = sh.pitch / ICP_LEAF, off = 0, l = 0;
+    for (;;) {
+        if (cnt == 1) {
+            sh.level_cnt[l] = 1; sh.level_off[l] = off; off += 1; sh.n_levels = l + 1;
+            break;
+        }
+        uint32_t padded = round_up(cnt, ICP_FAN);
+        sh.level_cnt[l] = padded; sh.level_off[l] = off; off += padded;
+        cnt = padded / ICP_FAN;
+        l++;
+    }
+    sh.nodes_per_seg = off;
+    return sh;
+}
+
+void icp_free_cloudset(CloudSet& cs) {
+    cudaFree(cs.pts); cudaFree(cs.nrm); cudaFree(cs.boxes); cudaFree(cs.pos_of_orig); cudaFree(cs.counts);
+    cudaFree(cs.bbox); cudaFree(cs.bb_lo); cudaFree(cs.bb_hi);
+    free(cs.h_counts);
+    cs = CloudSet();
+}
+
+int icp_build_cloudset(icpsymm_ctx* ctx, CloudSet& cs, const float* xyz, bool on_device, const uint32_t* counts,
+                       size_t nseg, size_t max_count, size_t stride_bytes) {
+    if (!xyz || nseg == 0 || max_count == 0) return icp_fail_msg(ctx, ICPSYMM_ERR_INVALID, "empty cloud");
+    if (stride_bytes < 12 || (stride_bytes & 3)) return icp_fail_msg(ctx, ICPSYMM_ERR_INVALID, "stride_bytes must be >= 12 and a multiple of 4");
+    if (max_count > 0x7ffffff0ull || nseg > 0x100000ull) return icp_fail_msg(ctx, ICPSYMM_ERR_INVALID, "cloud too large");
+    cudaStream_t st = ctx->stream;
+    cs.valid = false; cs.has_normals = false;
+    TreeShape sh = icp_make_shape((uint32_t)max_count);
+    size_t slots = nseg * (size_t)sh.pitch, nodes = nseg * (size_t)sh.nodes_per_seg;
+
+    // host copy of the counts
+    free(cs.h_counts);
+    cs.h_counts = (uint32_t*)malloc(sizeof(uint32_t) * nseg);
+    size_t total = 0;
+    for (size_t s = 0; s < nseg; s++) {
+        uint32_t c = counts ? counts[s] : (uint32_t)max_count;
+        if (c > max_count) return icp_fail_msg(ctx, ICPSYMM_ERR_INVALID, "counts[b] > max_count");
+        cs.h_counts[s] = c;
+        total += c;
+    }
+    int rc;
+    size_t cap;
+    cap = cs.cap_pts;  if ((rc = icp_reserve(ctx, &cs.pts, &cap, slots))) return rc;
+    cap = cs.cap_pts;  if ((rc = icp_reserve(ctx, &cs.nrm, &cap, slots))) return rc;
+    cap = cs.cap_pts;  if ((rc = icp_reserve(ctx, &cs.pos_of_orig, &cap, slots))) return rc;
+    cs.cap_pts = cap;
+    if ((rc = icp_reserve(ctx, &cs.boxes, &cs.cap_nodes, nodes))) return rc;
+    cap = cs.cap_seg;  if ((rc = icp_reserve(ctx, &cs.counts, &cap, nseg))) return rc;
+    cap = cs.cap_seg * 8; if ((rc = icp_reserve(ctx, &cs.bbox, &cap, nseg * 8))) return rc;
+    cap = cs.cap_seg;  if ((rc = icp_reserve(ctx, &cs.bb_lo, &cap, nseg))) return rc;
+    cap = cs.cap_seg;  if ((rc = icp_reserve(ctx, &cs.bb_hi, &cap, nseg))) return rc;
+    cs.cap_seg = cap;
+    cap = ctx->sort_cap; if ((rc = icp_reserve(ctx, &ctx->keys_a, &cap, slots))) return rc;
+    cap = ctx->sort_cap; if ((rc = icp_reserve(ctx, &ctx->keys_b, &cap, slots))) return rc;
+    cap = ctx->sort_cap; if ((rc = icp_reserve(ctx, &ctx->vals_a, &cap, slots))) return rc;
+    cap = ctx->sort_cap; if ((rc = icp_reserve(ctx, &ctx->vals_b, &cap, slots))) return rc;
+    ctx->sort_cap = cap;
+    if (!ctx->d_flags) ICP_CUDA_CHECK(cudaMalloc((void**)&ctx->d_flags, 4 * sizeof(int)));
+
+    const char* raw = reinterpret_cast<const char*>(xyz);
+    if (!on_device) {
+        size_t bytes = nseg * max_count * stride_bytes;
+        char* stg = (char*)ctx->staging;
+        if ((rc = icp_reserve(ctx, &stg, &ctx->staging_bytes, bytes))) return rc;
+        ctx->staging = stg;
+        ICP_CUDA_CHECK(cudaMemcpyAsync(stg, xyz, bytes, cudaMemcpyHostToDevice, st));
+        raw = stg;
+    }
+    ICP_CUDA_CHECK(cudaMemcpyAsync(cs.counts, cs.h_counts, sizeof(uint32_t) * nseg, cudaMemcpyHostToDevice, st));
+
+    const uint32_t ns = (uint32_t)nseg, mc = (uint32_t)max_count;
+    bbox_init_kernel<<<(ns * 8 + 255) / 256, 256, 0, st>>>(cs.bbox, ns, ctx->d_flags);
+    {
+        uint32_t bx = (uint32_t)((max_count + 256 * 8 - 1) / (256 * 8));
+        uint32_t cap_bx = (uint32_t)((ctx->sm_count * 8 + ns - 1) / ns);
+        if (bx > cap_bx) bx = cap_bx;
+        if (bx < 1) bx = 1;
+        dim3 grid(bx, ns);
+        bbox_kernel<<<grid, 256, 0, st>>>(raw, stride_bytes, cs.counts, mc, cs.bbox, ctx->d_flags);
+    }
+    bbox_finish_kernel<<<(ns + 127) / 128, 128, 0, st>>>(cs.bbox, cs.counts, cs.bb_lo, cs.bb_hi, ns);
+    const uint32_t gb = (uint32_t)((slots + 255) / 256);
+    morton_kernel<<<gb, 256, 0, st>>>(raw, stride_bytes, cs.counts, mc, sh.pitch, ns, cs.bb_lo, cs.bb_hi,
+                                      ctx->keys_a, ctx->vals_a);
+    int seg_bits = 0;
+    while ((1ull << seg_bits) < nseg) seg_bits++;
+    int end_bit = (nseg > 1) ? 32 + seg_bits : 31;
+    size_t temp_bytes = 0;
+    ICP_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, ctx->keys_a, ctx->keys_b, ctx->vals_a,
+                                                   ctx->vals_b, slots, 0, end_bit, st));
+    {
+        char* tmp = (char*)ctx->cub_temp;
+        if ((rc = icp_reserve(ctx, &tmp, &ctx->cub_temp_bytes, temp_bytes))) return rc;
+        ctx->cub_temp = tmp;
+    }
+    ICP_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(ctx->cub_temp, temp_bytes, ctx->keys_a, ctx->keys_b, ctx->vals_a,
+                                                   ctx->vals_b, slots, 0, end_bit, st));
+    gather_kernel<<<gb, 256, 0, st>>>(raw, stride_bytes, cs.counts, mc, sh.pitch, ns, ctx->vals_b, cs.pts,
+                                      cs.pos_of_orig);
+    {
+        size_t n0 = (size_t)ns * sh.level_cnt[0];
+        leaf_box_kernel<<<(uint32_t)((n0 + 255) / 256), 256, 0, st>>>(cs.pts, cs.boxes, sh, ns);
+        for (uint32_t l = 1; l < sh.n_levels; l++) {
+            size_t nl = (size_t)ns * sh.level_cnt[l];
+            upper_box_kernel<<<(uint32_t)((nl + 255) / 256), 256, 0, st>>>(cs.boxes, sh, ns, (int)l);
+        }
+    }
+    ICP_CUDA_CHECK(cudaGetLastError());
+    int h_flag = 0;
+    ICP_CUDA_CHECK(cudaMemcpyAsync(&h_flag, ctx->d_flags, sizeof(int), cudaMemcpyDeviceToHost, st));
+    ICP_CUDA_CHECK(cudaStreamSynchronize(st));
+    if (h_flag) return icp_fail_msg(ctx, ICPSYMM_ERR_NONFINITE, "cloud holds NaN/Inf coordinates");
+    cs.nseg = ns; cs.max_count = mc; cs.total = total; cs.shape = sh; cs.valid = true;
+    return ICPSYMM_OK;
+}

@@ -1,0 +1,133 @@
+// internal.h -- host-side structures shared by the translation units of libicpsymm_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "../../include/icpsymm.h"
+#include "common.cuh"
+
+// device storage of one cloud set (nseg independent clouds, fixed pitch)
+struct CloudSet {
+    uint32_t nseg = 0;
+    uint32_t max_count = 0;       // largest segment
+    size_t total = 0;             // sum of counts
+    TreeShape shape{};
+    float4* pts = nullptr;
+    float4* nrm = nullptr;
+    Box* boxes = nullptr;
+    uint32_t* pos_of_orig = nullptr;
+    uint32_t* counts = nullptr;   // device, nseg
+    uint32_t* bbox = nullptr;     // device, nseg*8 ordered-uint (lo xyz, pad, hi xyz, pad) during build
+    float4* bb_lo = nullptr;      // device, nseg
+    float4* bb_hi = nullptr;
+    uint32_t* h_counts = nullptr; // host copy
+    size_t cap_pts = 0, cap_nodes = 0, cap_seg = 0;
+    bool valid = false, has_normals = false;
+
+    CloudView view() const {
+        CloudView v;
+        v.pts = pts; v.nrm = nrm; v.boxes = boxes; v.pos_of_orig = pos_of_orig; v.counts = counts;
+        v.shape = shape; v.nseg = nseg;
+        return v;
+    }
+};
+
+struct GraphKey {
+    int max_iters = -1;
+    uint32_t nseg = 0, blocks_per_seg = 0, src_pitch = 0, tgt_pitch = 0;
+    const void *p0 = nullptr, *p1 = nullptr, *p2 = nullptr, *p3 = nullptr, *p4 = nullptr, *p5 = nullptr;
+    int comm_mode = 0, shard_rank = 0, shard_world = 1, trace = 0;
+    bool operator==(const GraphKey& o) const {
+        return max_iters == o.max_iters && nseg == o.nseg && blocks_per_seg == o.blocks_per_seg &&
+               src_pitch == o.src_pitch && tgt_pitch == o.tgt_pitch && p0 == o.p0 && p1 == o.p1 && p2 == o.p2 &&
+               p3 == o.p3 && p4 == o.p4 && p5 == o.p5 && comm_mode == o.comm_mode && shard_rank == o.shard_rank &&
+               shard_world == o.shard_world && trace == o.trace;
+    }
+};
+
+struct icpsymm_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    char err[512] = {0};
+
+    CloudSet src, tgt;
+
+    // build scratch (grow-only)
+    void* staging = nullptr;      size_t staging_bytes = 0;
+    unsigned long long *keys_a = nullptr, *keys_b = nullptr;
+    uint32_t *vals_a = nullptr, *vals_b = nullptr;
+    size_t sort_cap = 0;
+    void* cub_temp = nullptr;     size_t cub_temp_bytes = 0;
+    int* d_flags = nullptr;       // [0] non-finite count
+
+    // loop state
+    SegState* d_state = nullptr;  size_t state_cap = 0;
+    SegState* h_state = nullptr;  size_t h_state_cap = 0;   // pinned mirror
+    LoopParams* d_lp = nullptr;
+    uint32_t* corr_pos = nullptr; size_t corr_cap = 0;
+    double* partial = nullptr;    size_t partial_cap = 0;
+    double* gsum = nullptr;       size_t gsum_cap = 0;
+    float* trace_T = nullptr;     double* trace_diff = nullptr; size_t trace_cap = 0; int trace_stride = 0;
+    void* io_buf = nullptr;       size_t io_bytes = 0;   // device scratch for exports/imports
+    uint32_t last_blocks_per_seg = 0;
+    bool have_corr = false;
+
+    // options
+    double opt_rel_diff_tol = 0.0;
+    int opt_identity = 0;
+    float opt_max_pair_dist = 0.f;
+    int opt_use_graph = 1;
+    int opt_kernel_timing = 0;
+    int opt_warm_start = 1;
+    int opt_trace = 0;
+    int opt_grid_blocks = 0;
+
+    // graph cache
+    cudaGraphExec_t graph_exec = nullptr;
+    GraphKey graph_key;
+
+    // timing
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+    cudaEvent_t* ev_pool = nullptr; int ev_pool_n = 0;
+
+    // multi-GPU
+    int shard_rank = 0, shard_world = 1;
+    void* nccl_comm = nullptr;
+    void* nccl_lib = nullptr;
+};
+
+int icp_fail(icpsymm_ctx* ctx, cudaError_t e, const char* expr, const char* file, int line);
+int icp_fail_msg(icpsymm_ctx* ctx, int status, const char* msg);
+
+template <typename T>
+int icp_reserve(icpsymm_ctx* ctx, T** p, size_t* cap, size_t need);   // grow-only cudaMalloc, element counts
+
+// index_build.cu
+TreeShape icp_make_shape(uint32_t max_count);
+int icp_build_cloudset(icpsymm_ctx* ctx, CloudSet& cs, const float* xyz, bool on_device, const uint32_t* counts,
+                       size_t nseg, size_t max_count, size_t stride_bytes);
+void icp_free_cloudset(CloudSet& cs);
+
+// normals.cu
+int icp_estimate_normals(icpsymm_ctx* ctx, CloudSet& cs, int k, const float vp[3]);
+int icp_export_normals(icpsymm_ctx* ctx, const CloudSet& cs, float* out_host);
+int icp_import_normals(icpsymm_ctx* ctx, CloudSet& cs, const float* in_host);
+
+// icp_loop.cu
+int icp_run_loop(icpsymm_ctx* ctx, int max_iters, float thr, const float* T_init /*12 floats (3x4) or null*/,
+                 const double* origin /*3 or null*/, bool single_search, float* T_out, icpsymm_stats* stats);
+int icp_run_single(icpsymm_ctx* ctx, const float* T16, const double* origin, icpsymm_stats* stats);
+int icp_export_correspondences(icpsymm_ctx* ctx, int32_t* idx_out, float* d2_out);
+int icp_export_transformed(icpsymm_ctx* ctx, const float* T, float* xyz_out, size_t stride_bytes);
+int icp_solve_compose_device(icpsymm_ctx* ctx, const double* sums, const double* origin, double* Tinc, double* x,
+                             double* ratio);
+int icp_read_sums(icpsymm_ctx* ctx, double* sums, double* origin_out);
+
+// kabsch.cu
+int icp_kabsch(icpsymm_ctx* ctx, const double* src, const double* dst, size_t n, double R[9], double T[3]);
+
+// comm.cu
+int icp_comm_allreduce(icpsymm_ctx* ctx, double* buf, size_t count);

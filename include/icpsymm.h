@@ -1,0 +1,151 @@
+/*
+ * icpsymm.h -- C ABI of the B200-native symmetric-ICP registration path.
+ *
+ * This is the drop-in boundary for the hot path of StephenNG59/ICP-symm.  The reference has
+ * no FFI layer: its boundary is two C++ headers, ICP/myicp.h:7-36 (class MyICP) and
+ * ICP/regist.h:8 (registrateNPoint), whose types are PCL / OpenCV objects.  Every entry point
+ * below names the reference interface it replaces.  Plain pointers and sizes only: no CUDA,
+ * torch, PCL or OpenCV types.  The C++ facade that keeps the reference's class shape lives in
+ * icp-symm_b200/host/myicp.h + regist.h and is written purely on top of this ABI.
+ *
+ * Conventions
+ *   - xyz inputs: float, `stride_bytes` between consecutive points (12 for packed xyz, 16 for
+ *     pcl::PointXYZ-style x,y,z,pad -- myicp.h:5).  Host pointers unless the name ends in _dev.
+ *   - 4x4 transforms: float[16], ROW-major, map SOURCE -> TARGET (myicp.cpp:138 left-multiplies
+ *     increments: transform = incre * transform).
+ *   - normals: float[4] per point (nx, ny, nz, curvature), i.e. pcl::Normal.
+ *   - indices returned to the caller are ORIGINAL point indices (order of the arrays passed in).
+ *   - all calls on one context are serialised by the caller (one context per host thread).
+ *   - return value: ICPSYMM_OK (0), a positive warning, or a negative error.  No CPU fallback
+ *     exists: without a CUDA device every compute call returns ICPSYMM_ERR_CUDA.
+ */
+#ifndef ICPSYMM_H
+#define ICPSYMM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ICPSYMM_OK 0
+#define ICPSYMM_WARN_DEGENERATE 1    /* a 6x6 pivot was dropped (rank-deficient geometry) */
+#define ICPSYMM_ERR_INVALID (-1)     /* bad argument */
+#define ICPSYMM_ERR_CUDA (-2)        /* CUDA runtime error (see icpsymm_last_error) */
+#define ICPSYMM_ERR_NOT_READY (-3)   /* clouds or normals missing */
+#define ICPSYMM_ERR_SIZE (-4)        /* size mismatch (identity pairing needs equal sizes, func.cpp:21) */
+#define ICPSYMM_ERR_NONFINITE (-5)   /* NaN/Inf coordinate in an input cloud */
+#define ICPSYMM_ERR_COMM (-6)        /* NCCL / peer-exchange error */
+
+#define ICPSYMM_NSUMS 37             /* normal-equation vector length, layout in DESIGN.md */
+
+typedef struct icpsymm_ctx icpsymm_ctx;
+
+typedef struct icpsymm_stats {
+    int32_t iters;            /* solves applied (trips of the while loop, myicp.cpp:123) */
+    int32_t converged;        /* 1: diff <= threshold, 2: relative-diff tolerance, 0: hit max_iters */
+    int32_t degenerate;       /* a pivot was dropped in some iteration */
+    int32_t searches;         /* correspondence searches run (= iters + 1 unless stopped early) */
+    double diff;              /* sum_i ||T p_i - q_nn(i)|| of the final search (evalDiff, func.cpp:19-40) */
+    double rmse;              /* sqrt(mean d2) of the final search */
+    double min_pivot_ratio;   /* min over iterations of min_j d_j/A_jj (weak-constraint indicator) */
+    uint64_t pairs;           /* pairs used by the last solve */
+    float loop_ms;            /* device time of the whole loop, CUDA events on the context stream */
+    float search_ms;          /* summed duration of the NN+accumulate kernel (ICPSYMM_OPT_KERNEL_TIMING) */
+    float solve_ms;           /* summed duration of the reduce+solve kernel  (ICPSYMM_OPT_KERNEL_TIMING) */
+    int32_t search_launches;
+    int32_t solve_launches;
+    int32_t reserved;
+} icpsymm_stats;
+
+/* option keys for icpsymm_set_option */
+enum {
+    ICPSYMM_OPT_REL_DIFF_TOL = 1,   /* 0 = off (reference behaviour); stop when |d(k-1)-d(k)| <= tol*d(k-1) */
+    ICPSYMM_OPT_IDENTITY_PAIRS = 2, /* 1 = pair row i with row i (what myicp.cpp:128-131 actually does) */
+    ICPSYMM_OPT_MAX_PAIR_DIST = 3,  /* 0 = off; reject pairs farther than this */
+    ICPSYMM_OPT_USE_GRAPH = 4,      /* 1 (default) = run the loop as one CUDA graph */
+    ICPSYMM_OPT_KERNEL_TIMING = 5,  /* 1 = per-kernel CUDA-event timing (forces stream mode) */
+    ICPSYMM_OPT_WARM_START = 6,     /* 1 (default) = seed each search with the previous correspondence */
+    ICPSYMM_OPT_TRACE = 7,          /* 1 = keep per-search transform + diff (icpsymm_get_trace) */
+    ICPSYMM_OPT_GRID_BLOCKS = 8     /* blocks per pair for the search kernel, 0 = auto */
+};
+
+/* ---- lifetime (MyICP::MyICP / ~MyICP, myicp.cpp:6-18) ---- */
+int icpsymm_create(icpsymm_ctx** ctx, int device_ordinal);
+/* same, but all work is enqueued on the caller's cudaStream_t (passed as void*) */
+int icpsymm_create_on_stream(icpsymm_ctx** ctx, int device_ordinal, void* cuda_stream);
+void icpsymm_destroy(icpsymm_ctx* ctx);
+const char* icpsymm_status_string(int status);
+const char* icpsymm_last_error(const icpsymm_ctx* ctx);
+void* icpsymm_get_stream(const icpsymm_ctx* ctx); /* the cudaStream_t all work of this context runs on */
+int icpsymm_synchronize(icpsymm_ctx* ctx);
+int icpsymm_set_option(icpsymm_ctx* ctx, int key, double value);
+int icpsymm_device_info(int device_ordinal, int* sm_count, int* cc_major, int* cc_minor, size_t* total_mem);
+
+/* ---- clouds (MyICP::LoadCloud, myicp.cpp:20-31; pasteInMatrix, func.cpp:5-15) ----
+ * Copies the points to the device, Morton-sorts them and builds the search index.  Any normals
+ * of that cloud are invalidated. */
+int icpsymm_set_source(icpsymm_ctx* ctx, const float* xyz, size_t n, size_t stride_bytes);
+int icpsymm_set_target(icpsymm_ctx* ctx, const float* xyz, size_t n, size_t stride_bytes);
+int icpsymm_set_source_dev(icpsymm_ctx* ctx, const float* xyz_dev, size_t n, size_t stride_bytes);
+int icpsymm_set_target_dev(icpsymm_ctx* ctx, const float* xyz_dev, size_t n, size_t stride_bytes);
+/* batches of independent pairs: pair b occupies rows [b*max_count, b*max_count+counts[b]) of xyz;
+ * counts == NULL means every cloud holds max_count points. */
+int icpsymm_set_source_batch(icpsymm_ctx* ctx, const float* xyz, const uint32_t* counts, size_t n_pairs,
+                             size_t max_count, size_t stride_bytes);
+int icpsymm_set_target_batch(icpsymm_ctx* ctx, const float* xyz, const uint32_t* counts, size_t n_pairs,
+                             size_t max_count, size_t stride_bytes);
+
+/* ---- normals (MyICP::estimateNormals, myicp.cpp:152-172: NormalEstimation, setKSearch(10)) ----
+ * exact kNN-k (self included), covariance, eigenvector of the smallest eigenvalue, flipped towards
+ * `viewpoint` (NULL = (0,0,0), PCL's default), curvature in .w.  3 <= k <= 32. */
+int icpsymm_estimate_normals(icpsymm_ctx* ctx, int k, const float viewpoint[3]);
+/* which: 0 = source, 1 = target.  normals4: n x 4 floats in original point order. */
+int icpsymm_set_normals(icpsymm_ctx* ctx, int which, const float* normals4);
+int icpsymm_get_normals(icpsymm_ctx* ctx, int which, float* normals4);
+
+/* ---- registration (MyICP::RegisterSymm, myicp.cpp:100-150, with the parameters its
+ * "todo add params to specify iters & diff" asks for, myicp.h:19).  Reference defaults: 10, 1.0f. ----
+ * while (diff > diff_threshold && iters++ < max_iters) { correspondences; estimateTransformSymm;
+ * apply; transform = incre * transform; diff = evalDiff }.  T_out: 16 floats (n_pairs*16 for a batch),
+ * stats: one record (n_pairs records for a batch); both may be NULL. */
+int icpsymm_register_symm(icpsymm_ctx* ctx, int max_iters, float diff_threshold, float* T_out,
+                          icpsymm_stats* stats);
+
+/* ---- building blocks of the loop, exposed because the reference exposes them (func.h:5-27) ---- */
+/* the missing search of myicp.cpp:128-131: exact 1-NN of T*source in target, lowest index on ties.
+ * idx_out: n_source int32 (original target indices), d2_out (optional): fp32 squared distances. */
+int icpsymm_find_correspondences(icpsymm_ctx* ctx, const float T[16], int32_t* idx_out, float* d2_out);
+/* correspondences / distances of the last search run by icpsymm_register_symm */
+int icpsymm_get_correspondences(icpsymm_ctx* ctx, int32_t* idx_out, float* d2_out);
+/* evalDiff(src, tgt, indices) (func.cpp:36-40, a stub in the reference): sum ||T p - q_nn|| */
+int icpsymm_eval_diff(icpsymm_ctx* ctx, const float T[16], double* diff);
+/* calculateMatrixNotation + the normal equations (func.cpp:43-60): the 37 raw sums about `origin`
+ * for the pairs found under T (pair 0 of a batch). */
+int icpsymm_normal_equations(icpsymm_ctx* ctx, const float T[16], const double origin[3],
+                             double sums[ICPSYMM_NSUMS]);
+/* estimateTransformSymm's solve + composition (func.cpp:76-102) for a given sums vector, on device */
+int icpsymm_solve_compose(icpsymm_ctx* ctx, const double sums[ICPSYMM_NSUMS], const double origin[3],
+                          double Tinc[16], double x[6], double* min_pivot_ratio);
+/* applyTransform (func.cpp:104-121) of the source by T, original order, `stride_bytes` between points */
+int icpsymm_get_transformed_source(icpsymm_ctx* ctx, const float T[16], float* xyz_out, size_t stride_bytes);
+/* per-search trace (ICPSYMM_OPT_TRACE): k = 0..searches-1 of pair `pair` */
+int icpsymm_get_trace(icpsymm_ctx* ctx, size_t pair, int k, float T[16], double* diff);
+
+/* ---- closed-form point-to-point fit (registrateNPoint, regist.h:8-72): dst = R src + T, fp64 ---- */
+int icpsymm_register_npoint(icpsymm_ctx* ctx, const double* src_xyz, const double* dst_xyz, size_t n,
+                            double R[9], double T[3]);
+
+/* ---- multi-GPU.  Pair batches need nothing: each rank registers its own pairs.
+ * Query sharding: every rank holds the full clouds; rank r searches the r-th slice of the sorted
+ * source and the 37-value normal equations are summed across ranks before the solve. ---- */
+int icpsymm_comm_unique_id(void* id_out128);                       /* ncclGetUniqueId on the root */
+int icpsymm_comm_init(icpsymm_ctx* ctx, const void* id128, int n_ranks, int rank);
+int icpsymm_comm_destroy(icpsymm_ctx* ctx);
+int icpsymm_set_query_shard(icpsymm_ctx* ctx, int rank, int n_ranks); /* without comm: shard only */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ICPSYMM_H */

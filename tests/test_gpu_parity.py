@@ -1,0 +1,392 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same inputs.
+
+Bars (BASELINE.json north_star): nearest-neighbour indices bit-exact (ties -> lowest index),
+fp32 squared distances bit-exact, final transform rotation <= 1e-5 rad, translation <= 1e-5 x
+cloud extent, RMSE relative <= 1e-5.
+"""
+import numpy as np
+import pytest
+
+import icpsymm as icp
+import workloads as wl
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+ROT_TOL = 1e-5          # rad
+TRANS_TOL = 1e-5        # x extent
+RMSE_RTOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = icp.Context(0)
+    yield c
+    c.close()
+
+
+def _rand_T(rng, scale=1.0, max_deg=40.0):
+    R = wl.rotation(rng.standard_normal(3), rng.uniform(-max_deg, max_deg))
+    T = np.eye(4)
+    T[:3, :3] = R
+    T[:3, 3] = rng.standard_normal(3) * scale
+    return T.astype(np.float32)
+
+
+def _check_nn(ctx, src, tgt, T=None):
+    """device search under T == oracle search of the oracle-transformed points, bit for bit"""
+    ctx.set_source(src)
+    ctx.set_target(tgt)
+    idx, d2 = ctx.find_correspondences(T)
+    Tf = np.eye(4, dtype=np.float32) if T is None else np.asarray(T, np.float32)
+    p = orc.transform_points(Tf, src)
+    oi, od = (orc.nn_brute(p, tgt) if len(tgt) * len(src) <= 4e7 else orc.KdTree(tgt).nn(p))
+    assert np.array_equal(idx, oi), f"{(idx != oi).sum()} of {len(idx)} indices differ"
+    assert np.array_equal(d2, od)
+    return idx, d2
+
+
+def test_device_is_blackwell():
+    info = icp.device_info(0)
+    assert info["cc"][0] >= 10, info
+
+
+def test_nn_cat_golden(ctx, cat, cat_out, gold):
+    idx, d2 = _check_nn(ctx, cat, cat_out)
+    assert np.array_equal(idx, gold["nn_idx"]) and np.array_equal(d2, gold["nn_d2"])
+    assert np.array_equal(idx, gold["flann_idx"])        # OpenCV FLANN KDTREE_SINGLE agrees too
+    assert ctx.eval_diff() == pytest.approx(np.sqrt(gold["nn_d2"].astype(np.float64)).sum(), rel=1e-6)
+
+
+def test_nn_under_transforms(ctx, cat, cat_out, bunny):
+    rng = np.random.default_rng(11)
+    for _ in range(4):
+        _check_nn(ctx, cat, cat_out, _rand_T(rng, 20.0))
+    tgt, _ = wl.config_bunny(bunny)
+    _check_nn(ctx, bunny, tgt)
+    _check_nn(ctx, bunny, tgt, _rand_T(rng, 0.1, 10))
+
+
+def test_nn_ties_lowest_index(ctx):
+    g = np.stack(np.meshgrid(*[np.arange(9)] * 3, indexing="ij"), -1).reshape(-1, 3).astype(np.float32)
+    tgt = np.concatenate([g, g[::-1], g[:100]])            # every point duplicated: ties everywhere
+    q = np.concatenate([g + 0.5, g, g * 0.5 + 0.25]).astype(np.float32)
+    idx, _ = _check_nn(ctx, q, tgt)
+    assert (idx < len(g)).all()                           # the first copy always wins
+
+
+@pytest.mark.parametrize("n,m", [(1, 1), (1, 9), (7, 3), (8, 8), (9, 65), (63, 511), (64, 513), (257, 4097),
+                                 (1000, 37), (5000, 20000)])
+def test_nn_ragged_sizes(ctx, n, m):
+    rng = np.random.default_rng(n * 100003 + m)
+    _check_nn(ctx, rng.standard_normal((n, 3)).astype(np.float32), rng.standard_normal((m, 3)).astype(np.float32))
+
+
+def test_nn_far_queries_and_clusters(ctx):
+    rng = np.random.default_rng(5)
+    tgt = np.concatenate([rng.standard_normal((30000, 3)) * 0.01 + c for c in ([0, 0, 0], [5, 5, 5], [-3, 8, 1])]).astype(np.float32)
+    q = (rng.standard_normal((20000, 3)) * 6).astype(np.float32)
+    _check_nn(ctx, q, tgt)
+    # pcl::PointXYZ-style 16-byte stride (myicp.h:5)
+    q4 = np.zeros((len(q), 4), np.float32); q4[:, :3] = q
+    ctx.set_source(q4[:, :3])                              # strided view, stride 16
+    idx, _ = ctx.find_correspondences()
+    assert np.array_equal(idx, orc.KdTree(tgt).nn(q)[0])
+
+
+def test_nn_synth_200k(ctx):
+    src, tgt, T = wl.config_synth(200_000)
+    _check_nn(ctx, src, tgt)                               # far queries (30 deg / 0.1 extent)
+    _check_nn(ctx, src, tgt, T.astype(np.float32))         # near queries (aligned)
+
+
+def _angle(a, b):
+    a, b = a.astype(np.float64), b.astype(np.float64)
+    return np.arctan2(np.linalg.norm(np.cross(a, b), axis=1), np.abs(np.einsum("ni,ni->n", a, b)))
+
+
+def test_normals_parity(ctx, cat, cat_out):
+    src, tgt, _ = wl.config_synth(50_000)
+    for a, b in ((cat, cat_out), (src, tgt)):
+        ctx.set_source(a)
+        ctx.set_target(b)
+        ctx.estimate_normals(10)
+        for which, xyz in ((0, a), (1, b)):
+            dn = ctx.get_normals(which)
+            on, gap = orc.estimate_normals(xyz, 10)
+            ok = gap > 1e-3
+            ang = _angle(dn[ok, :3], on[ok, :3])
+            assert ang.max() < 1e-4, f"max normal angle {ang.max():.3e} rad"
+            assert (np.einsum("ni,ni->n", dn[ok, :3], on[ok, :3]) > 0).mean() > 0.9999
+            assert np.allclose(dn[ok, 3], on[ok, 3], atol=2e-5)
+            assert np.allclose(np.linalg.norm(dn[:, :3], axis=1), 1.0, atol=1e-5)
+
+
+def test_normals_k_variants_and_small_clouds(ctx):
+    rng = np.random.default_rng(3)
+    P = np.c_[rng.uniform(-1, 1, (3000, 2)), np.zeros(3000)].astype(np.float32)
+    P[:, 2] = 0.05 * np.sin(3 * P[:, 0])
+    ctx.set_source(P)
+    ctx.set_target(P[:5])                                  # fewer points than k
+    for k in (5, 10, 16, 24):
+        ctx.estimate_normals(k, viewpoint=(0, 0, 10))
+        dn = ctx.get_normals(0)
+        on, gap = orc.estimate_normals(P, k, viewpoint=(0, 0, 10))
+        ok = gap > 1e-3
+        assert _angle(dn[ok, :3], on[ok, :3]).max() < 1e-4
+        assert (dn[:, 2] > 0).all()                        # flipped towards the viewpoint above the sheet
+        tn = ctx.get_normals(1)
+        assert np.isfinite(tn).all()
+
+
+def test_normal_equations_match_oracle_and_literal_rows(ctx, cat, cat_out):
+    ctx.set_source(cat)
+    ctx.set_target(cat_out)
+    ctx.estimate_normals(10)
+    ns, nt = ctx.get_normals(0), ctx.get_normals(1)
+    rng = np.random.default_rng(2)
+    for T, origin in ((None, (0.0, 0.0, 0.0)), (_rand_T(rng, 5.0, 10), (3.0, 20.0, 30.0))):
+        S = ctx.normal_equations(T, origin)
+        Tf = np.eye(4, dtype=np.float32) if T is None else T
+        p, npn = orc.transform_points(Tf, cat), orc.rotate_vectors(Tf, ns)
+        idx, _ = orc.nn_brute(p, cat_out)
+        So = orc.symm_accumulate(p, npn, cat_out[idx], nt[idx], origin)
+        scale = np.abs(So).max()
+        assert np.allclose(S, So, rtol=2e-5, atol=1e-6 * scale), np.abs(S - So).max() / scale
+        assert S[36] == len(cat)
+    # identity pairing + origin 0 is exactly the sum of calculateMatrixNotation's rows (func.cpp:43-60)
+    ctx.set_option(icp.OPT_IDENTITY_PAIRS, 1)
+    try:
+        S = ctx.normal_equations(None, (0, 0, 0))
+    finally:
+        ctx.set_option(icp.OPT_IDENTITY_PAIRS, 0)
+    M, N, c = orc.matrix_notation(cat, ns[:, :3], cat_out, nt[:, :3])
+    M, N, c = M.astype(np.float64), N.astype(np.float64), c.astype(np.float64)
+    iu = np.triu_indices(3)
+    assert np.allclose(S[0:6], (M.T @ M)[iu], rtol=2e-5)
+    assert np.allclose(S[15:21], (N.T @ N)[iu], rtol=2e-5)
+    assert np.allclose(S[21:24], M.T @ c, rtol=2e-5) and np.allclose(S[24:27], N.T @ c, rtol=2e-5)
+    assert S[33] == pytest.approx(orc.eval_diff(cat, cat_out), rel=1e-6)    # evalDiff, func.cpp:19-32
+
+
+def test_solve_compose_device_vs_oracle(ctx, cat, cat_out, gold):
+    ns, nt = gold["normals_cat"], gold["normals_cat_out"]
+    for origin in ((0.0, 0.0, 0.0), (5.0, 20.0, 30.0)):
+        S = orc.symm_accumulate(cat, ns, cat_out, nt, origin)
+        To, xo, dego = orc.solve_compose(S, origin)
+        Td, xd, rc, ratio = ctx.solve_compose(S, origin)
+        assert rc == dego == 0 and np.allclose(xd, xo, rtol=1e-10, atol=1e-12) and np.allclose(Td, To, atol=1e-10)
+        assert ratio == pytest.approx(orc.solve_compose.last_min_pivot_ratio, rel=1e-9)
+    # rank-deficient: a plane
+    rng = np.random.default_rng(1)
+    P = np.c_[rng.uniform(-1, 1, (500, 2)), np.zeros(500)].astype(np.float32)
+    n4 = np.tile(np.array([0, 0, 1, 0], np.float32), (500, 1))
+    S = orc.symm_accumulate(P, n4, P + np.float32([0, 0, 0.01]), n4)
+    Td, xd, rc, _ = ctx.solve_compose(S)
+    To, xo, dego = orc.solve_compose(S)
+    assert rc == icp.WARN_DEGENERATE and dego == 1 and np.isfinite(Td).all() and np.allclose(Td, To, atol=1e-12)
+
+
+def _register_and_compare(ctx, src, tgt, max_iters, thr, rel_tol=0.0, T_true=None, check_trace=True, match_iters=False):
+    ctx.set_source(src)
+    ctx.set_target(tgt)
+    ctx.estimate_normals(10)
+    ns, nt = ctx.get_normals(0), ctx.get_normals(1)
+    ctx.set_option(icp.OPT_TRACE, 1)
+    ctx.set_option(icp.OPT_REL_DIFF_TOL, rel_tol)
+    try:
+        T, st, rc = ctx.register_symm(max_iters, thr)
+        if match_iters:   # a relative-change stop can fall either side of a rounding error: pin the trip count
+            r = orc.register_symm(src, ns, tgt, nt, max_iters=st["iters"], diff_threshold=-1.0)
+            assert 0 < st["iters"] < max_iters
+        else:
+            r = orc.register_symm(src, ns, tgt, nt, max_iters=max_iters, diff_threshold=thr, rel_diff_tol=rel_tol)
+            assert st["converged"] == r["converged"], (st, r["converged"])
+        assert st["iters"] == r["iters"], (st, r["iters"])
+        ext = wl.extent(tgt)
+        assert wl.rotation_angle(T, r["T"]) <= ROT_TOL
+        assert np.abs(T[:3, 3].astype(np.float64) - r["T"][:3, 3]).max() <= TRANS_TOL * ext
+        assert st["rmse"] == pytest.approx(r["rmse"], rel=RMSE_RTOL, abs=1e-7 * ext)
+        assert st["diff"] == pytest.approx(r["diff"], rel=1e-4, abs=1e-6 * ext * len(src))
+        # correspondences of the final search: bit-exact against the oracle fed with the device transform
+        idx, d2 = ctx.get_correspondences()
+        p = orc.transform_points(T, src)
+        oi, od = orc.KdTree(tgt).nn(p)
+        assert np.array_equal(idx, oi) and np.array_equal(d2, od)
+        if check_trace:
+            for k in range(st["searches"]):
+                Tk, dk = ctx.trace(k)
+                oi, od = orc.KdTree(tgt).nn(orc.transform_points(Tk, src))
+                assert dk == pytest.approx(np.sqrt(od.astype(np.float64)).sum(), rel=1e-6)
+        if T_true is not None:
+            assert wl.rotation_angle(T, T_true) < 1e-4
+    finally:
+        ctx.set_option(icp.OPT_TRACE, 0)
+        ctx.set_option(icp.OPT_REL_DIFF_TOL, 0.0)
+    return T, st
+
+
+def test_register_cat_matches_oracle_and_truth(ctx, cat, cat_out, gold):
+    T, st = _register_and_compare(ctx, cat, cat_out, 50, 1.0)
+    assert st["iters"] == 5 and st["converged"] == 1 and st["degenerate"] == 0
+    # the reference's only known answer: Rz(45 deg), t = (2.5, 0, 0)  (main.cpp:44-52)
+    assert wl.rotation_angle(T, gold["truth_R"]) < 1e-5
+    assert np.abs(T[:3, 3] - gold["truth_t"]).max() < 1e-5 * wl.extent(cat)
+    # reference defaults (myicp.cpp:6): 10 iterations, threshold 1.0
+    T10, st10, _ = ctx.register_symm()
+    assert st10["iters"] == 5 and np.array_equal(T10, T)
+
+
+def test_register_stream_mode_equals_graph_mode(ctx, cat, cat_out):
+    ctx.set_source(cat); ctx.set_target(cat_out); ctx.estimate_normals(10)
+    Tg, sg, _ = ctx.register_symm(50, 1.0)
+    ctx.set_option(icp.OPT_USE_GRAPH, 0)
+    ctx.set_option(icp.OPT_KERNEL_TIMING, 1)
+    try:
+        Ts, ss, _ = ctx.register_symm(50, 1.0)
+    finally:
+        ctx.set_option(icp.OPT_USE_GRAPH, 1)
+        ctx.set_option(icp.OPT_KERNEL_TIMING, 0)
+    assert np.array_equal(Tg, Ts) and sg["iters"] == ss["iters"] and sg["diff"] == ss["diff"]
+    assert ss["search_launches"] == ss["searches"] and ss["search_ms"] > 0
+    # warm start off must not change any result
+    ctx.set_option(icp.OPT_WARM_START, 0)
+    try:
+        Tc, sc, _ = ctx.register_symm(50, 1.0)
+    finally:
+        ctx.set_option(icp.OPT_WARM_START, 1)
+    assert np.array_equal(Tg, Tc) and sc["diff"] == sg["diff"]
+
+
+def test_register_identity_pairs_and_zero_trip(ctx, cat, cat_out, gold):
+    ctx.set_source(cat); ctx.set_target(cat_out); ctx.estimate_normals(10)
+    ctx.set_option(icp.OPT_IDENTITY_PAIRS, 1)
+    try:
+        T, st, _ = ctx.register_symm(10, 1.0)
+        assert st["iters"] == 1 and wl.rotation_angle(T, gold["truth_R"]) < 1e-5
+        ctx.set_target(cat_out[:-1])
+        with pytest.raises(icp.IcpError) as e:
+            ctx.register_symm(10, 1.0)
+        assert e.value.status == icp.ERR_SIZE                                        # func.cpp:21 assert
+    finally:
+        ctx.set_option(icp.OPT_IDENTITY_PAIRS, 0)
+    # already aligned: zero trips, identity result (myicp.cpp:123)
+    ctx.set_source(cat); ctx.set_target(cat); ctx.estimate_normals(10)
+    T, st, _ = ctx.register_symm(10, 1.0)
+    assert st["iters"] == 0 and st["converged"] == 1 and np.array_equal(T, np.eye(4, dtype=np.float32))
+
+
+def test_register_bunny_config2(ctx, bunny):
+    tgt, Ttrue = wl.config_bunny(bunny)
+    ctx.set_source(bunny); ctx.set_target(tgt); ctx.estimate_normals(10)
+    T, st, rc = ctx.register_symm(10, 1e-6)
+    assert np.isfinite(T).all() and np.isfinite(st["diff"])
+    idx, d2 = ctx.get_correspondences()
+    oi, od = orc.nn_brute(orc.transform_points(T, bunny), tgt)
+    assert np.array_equal(idx, oi) and np.array_equal(d2, od)
+    assert st["rmse"] == pytest.approx(np.sqrt(od.astype(np.float64).mean()), rel=1e-5)
+    # exactly collinear input with consistent normals: flagged, finite
+    line = np.c_[np.linspace(0, 1, 200), np.zeros(200), np.zeros(200)].astype(np.float32)
+    n4 = np.tile(np.array([0, 0, 1, 0], np.float32), (200, 1))
+    ctx.set_source(line); ctx.set_target(line + np.float32([0, 0, 0.01]))
+    ctx.set_normals(0, n4); ctx.set_normals(1, n4)
+    T, st, rc = ctx.register_symm(3, 1e-9)
+    assert rc == icp.WARN_DEGENERATE and st["degenerate"] == 1 and np.isfinite(T).all()
+
+
+def test_register_synth_100k(ctx):
+    src, tgt, Ttrue = wl.config_synth(100_000)
+    _register_and_compare(ctx, src, tgt, 50, 1.0, rel_tol=1e-5, T_true=Ttrue, check_trace=False, match_iters=True)
+
+
+def test_max_pair_distance_rejection(ctx, cat, cat_out):
+    ctx.set_source(cat); ctx.set_target(cat_out); ctx.estimate_normals(10)
+    ns, nt = ctx.get_normals(0), ctx.get_normals(1)
+    ctx.set_option(icp.OPT_MAX_PAIR_DIST, 25.0)
+    try:
+        T, st, _ = ctx.register_symm(3, 1.0)
+    finally:
+        ctx.set_option(icp.OPT_MAX_PAIR_DIST, 0.0)
+    r = orc.register_symm(cat, ns, cat_out, nt, max_iters=3, diff_threshold=1.0, max_pair_dist=25.0)
+    assert st["iters"] == r["iters"] and st["pairs"] == r["pairs"]
+    assert wl.rotation_angle(T, r["T"]) <= 1e-4 and np.allclose(T[:3, 3], r["T"][:3, 3], atol=1e-3)
+
+
+def test_batch_equals_single_pairs(ctx):
+    pairs = [wl.config_batch_pair(b, 4096) for b in range(6)]
+    counts = np.array([4096, 4000, 4096, 1234, 4096, 9], np.uint32)
+    S = np.zeros((6, 4096, 3), np.float32); Tg = np.zeros((6, 4096, 3), np.float32)
+    for b, (s, t, _) in enumerate(pairs):
+        S[b, :counts[b]] = s[:counts[b]]; Tg[b, :counts[b]] = t[:counts[b]]
+    ctx.set_source_batch(S, counts); ctx.set_target_batch(Tg, counts)
+    ctx.estimate_normals(10)
+    Tb, stb, _ = ctx.register_symm(30, 1e-3)
+    idxb, _ = ctx.get_correspondences()
+    idxb = idxb.reshape(6, 4096)
+    for b in range(6):
+        c = int(counts[b])
+        ctx.set_source(S[b, :c]); ctx.set_target(Tg[b, :c]); ctx.estimate_normals(10)
+        T1, st1, _ = ctx.register_symm(30, 1e-3)
+        i1, _ = ctx.get_correspondences()
+        assert np.array_equal(Tb[b], T1), b
+        assert stb[b]["iters"] == st1["iters"] and stb[b]["diff"] == st1["diff"]
+        assert np.array_equal(idxb[b, :c], i1)
+        if c > 1000:
+            assert wl.rotation_angle(T1, pairs[b][2]) < 5e-3
+
+
+def test_query_shards_sum_to_whole(ctx, cat, cat_out):
+    """the per-shard normal-equation vectors add up to the single-GPU vector"""
+    ctx.set_source(cat); ctx.set_target(cat_out); ctx.estimate_normals(10)
+    whole = ctx.normal_equations(None, (0, 0, 0))
+    idx_whole, _ = ctx.find_correspondences()
+    parts, idx = [], np.full(len(cat), -1, np.int32)
+    for world in (2, 3):
+        parts = []
+        idx[:] = -1
+        for r in range(world):
+            ctx.set_query_shard(r, world)
+            parts.append(ctx.normal_equations(None, (0, 0, 0)))
+            i, _ = ctx.get_correspondences()
+            assert ((idx >= 0) & (i >= 0)).sum() == 0       # shards are disjoint
+            idx = np.where(i >= 0, i, idx)
+        ctx.set_query_shard(0, 1)
+        assert np.array_equal(idx, idx_whole)
+        assert np.allclose(np.sum(parts, axis=0), whole, rtol=1e-5, atol=1e-6 * np.abs(whole).max())  # fp32 reassociation
+
+
+def test_register_npoint_regist_h(ctx, cat, cat_out, gold):
+    R, T = ctx.register_npoint(cat, cat_out)
+    rc, Ro, To = orc.registrate_npoint(cat, cat_out)
+    assert np.allclose(R, Ro, atol=1e-10) and np.allclose(T, To, atol=1e-8)
+    assert wl.rotation_angle(R, gold["truth_R"]) < 1e-7 and np.abs(T - gold["truth_t"]).max() < 1e-6
+    with pytest.raises(icp.IcpError):
+        ctx.register_npoint(cat[:2], cat_out[:2])
+    rng = np.random.default_rng(0)
+    P = rng.standard_normal((100000, 3)); Rt = wl.rotation((1, 2, 3), 77.0); t = np.array([1.0, -2.0, 3.0])
+    R, T = ctx.register_npoint(P, P @ Rt.T + t)
+    assert np.allclose(R, Rt, atol=1e-12) and np.allclose(T, t, atol=1e-12)
+
+
+def test_transformed_source_is_apply_transform(ctx, cat):
+    ctx.set_source(cat)
+    T = _rand_T(np.random.default_rng(9), 3.0)
+    assert np.array_equal(ctx.transformed_source(T), orc.transform_points(T, cat))
+
+
+def test_errors_are_reported_not_hidden(ctx, cat):
+    c = icp.Context(0)
+    with pytest.raises(icp.IcpError) as e:
+        c.register_symm()
+    assert e.value.status == icp.ERR_NOT_READY
+    c.set_source(cat); c.set_target(cat)
+    with pytest.raises(icp.IcpError) as e:
+        c.register_symm()                                   # normals missing
+    assert e.value.status == icp.ERR_NOT_READY
+    bad = cat.copy(); bad[7, 1] = np.nan
+    with pytest.raises(icp.IcpError) as e:
+        c.set_target(bad)
+    assert e.value.status == icp.ERR_NONFINITE
+    with pytest.raises(icp.IcpError):
+        c.set_source(np.zeros((0, 3), np.float32))
+    c.close()
