@@ -481,13 +481,13 @@ int icp_run_loop(icpsymm_ctx* ctx, int max_iters, float thr, const float* T_init
     CloudSet& T = ctx->tgt;
     if (!S.valid || !T.valid) return icp_fail_msg(ctx, ICPSYMM_ERR_NOT_READY, "set_source / set_target first");
     if (S.nseg != T.nseg) return icp_fail_msg(ctx, ICPSYMM_ERR_SIZE, "source and target hold a different number of pairs");
-    if (!single_search && (!S.has_normals || !T.has_normals))
-        return icp_fail_msg(ctx, ICPSYMM_ERR_NOT_READY, "normals missing: call icpsymm_estimate_normals or icpsymm_set_normals");
     if (max_iters < 0) return icp_fail_msg(ctx, ICPSYMM_ERR_INVALID, "max_iters < 0");
     if (ctx->opt_identity)
         for (uint32_t s = 0; s < S.nseg; s++)
             if (S.h_counts[s] != T.h_counts[s])
                 return icp_fail_msg(ctx, ICPSYMM_ERR_SIZE, "identity pairing needs equal cloud sizes (func.cpp:21)");
+    if (!single_search && (!S.has_normals || !T.has_normals))
+        return icp_fail_msg(ctx, ICPSYMM_ERR_NOT_READY, "normals missing: call icpsymm_estimate_normals or icpsymm_set_normals");
     const uint32_t nseg = S.nseg;
     cudaStream_t st = ctx->stream;
     int rc;
