@@ -2,10 +2,11 @@
 //
 // Data layout in HBM (DESIGN.md "Layout"): every cloud set is a batch of `nseg` independent
 // clouds ("segments"; a single pair is nseg = 1) stored with a fixed pitch of P points:
-//   pts[seg*P + j]  float4  Morton-sorted point j of the segment, .w = original index bits
+//   pts[seg*P + j]  float4  Hilbert-sorted point j of the segment, .w = original index bits
 //   nrm[seg*P + j]  float4  (nx, ny, nz, curvature) of the same sorted point
-//   boxes[seg*nodes_per_seg + level_off[l] + i]  tight AABB of node i at level l of the implicit
-//       F-ary hierarchy over the sorted points (level 0 = groups of LEAF consecutive points)
+//   nodes[seg*nodes_per_seg + level_off[l] + i]  wide node i of level l >= 1 of the implicit 8-ary
+//       hierarchy over the sorted points: the tight AABBs of its 8 children in SoA form (192 B);
+//       level 0 = groups of LEAF consecutive points, whose boxes live in the level-1 records
 // Rounding contract: distances and transforms use separately rounded fp32
 // mul/add (no FMA) so that the CPU oracle computes bit-identical values.
 #pragma once
@@ -17,30 +18,32 @@
 #define ICP_LEAF (1 << ICP_LOG_LEAF)     // points per leaf group (8 * 16 B = one 128 B line)
 #define ICP_LOG_FAN 3
 #define ICP_FAN (1 << ICP_LOG_FAN)       // children per node
-#define ICP_MAX_LEVELS 12
+#define ICP_MAX_LEVELS 9                 // level 0 + 8 internal levels (8 pending-mask bytes): 8^9 points
 #define ICP_NSUMS 37
 #define ICP_PART_STRIDE 40               // doubles per partial-sum row (37 padded)
 #define ICP_INVALID_ID 0x7fffffff
 
-struct __align__(32) Box {
-    float4 lo;  // .w unused
-    float4 hi;
+// boxes of the 8 children of one internal node, structure-of-arrays so that one node is 12
+// independent 16-byte loads and the 8 bounds are computed together
+struct __align__(16) WideNode {
+    float lox[ICP_FAN], loy[ICP_FAN], loz[ICP_FAN];
+    float hix[ICP_FAN], hiy[ICP_FAN], hiz[ICP_FAN];
 };
 
 // shape of the implicit hierarchy, identical for every segment of a cloud set
 struct TreeShape {
     uint32_t pitch;                       // P: points per segment (multiple of ICP_LEAF)
     uint32_t n_levels;                    // levels above and including the leaf-group level; root = n_levels-1
-    uint32_t level_off[ICP_MAX_LEVELS];   // offset of level l inside a segment's node array
+    uint32_t level_off[ICP_MAX_LEVELS];   // offset of level l (>= 1) inside a segment's record array
     uint32_t level_cnt[ICP_MAX_LEVELS];   // padded node count of level l (multiple of ICP_FAN, root = 1)
-    uint32_t nodes_per_seg;
+    uint32_t nodes_per_seg;               // records per segment = sum of level_cnt[1..]
 };
 
 // device view of a cloud set
 struct CloudView {
     const float4* pts;
     const float4* nrm;
-    const Box* boxes;
+    const WideNode* nodes;
     const uint32_t* pos_of_orig;          // seg*P + original index -> sorted position
     const uint32_t* counts;               // points per segment
     TreeShape shape;

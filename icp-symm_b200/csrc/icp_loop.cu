@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(kNNThreads) nn_accum_kernel(const __grid_const
     const float4* __restrict__ snrm = P.src.nrm + (size_t)seg * P.src.shape.pitch;
     const float4* __restrict__ tpts = P.tgt.pts + (size_t)seg * P.tgt.shape.pitch;
     const float4* __restrict__ tnrm = P.tgt.nrm + (size_t)seg * P.tgt.shape.pitch;
-    const Box* __restrict__ tbox = P.tgt.boxes + (size_t)seg * P.tgt.shape.nodes_per_seg;
+    const WideNode* __restrict__ tbox = P.tgt.nodes + (size_t)seg * P.tgt.shape.nodes_per_seg;
     uint32_t* corr = P.corr_pos + (size_t)seg * P.src.shape.pitch;
     const uint32_t ntiles = (qhi - qlo + kNNThreads - 1) / kNNThreads;
 
@@ -132,7 +132,6 @@ __global__ void __launch_bounds__(kNNThreads) nn_accum_kernel(const __grid_const
             } else {
                 uint32_t prev = lp.warm_start ? corr[i] : 0xffffffffu;
                 if (prev < nt) best_offer(b, ldg4(tpts + prev), prev, p.x, p.y, p.z);
-                else greedy_descent(P.tgt.shape, tbox, tpts, p.x, p.y, p.z, b);
                 nn_traverse(P.tgt.shape, tbox, tpts, p.x, p.y, p.z, b);
             }
             corr[i] = b.pos;
@@ -188,64 +187,75 @@ __global__ void __launch_bounds__(kNNThreads) nn_accum_kernel(const __grid_const
 // ------------------------------------------------------------------------------------------------
 // K2: reduce + decide + solve + compose
 // ------------------------------------------------------------------------------------------------
-__device__ void mat34_mul(const double* A, const double* B, double* C) {  // C = A*B as 4x4 affine, 3x4 storage
-    double R[12];
+__device__ __forceinline__ void mat34_mul(const double (&A)[12], const double (&B)[12], double (&C)[12]) {
+    // C = A*B as 4x4 affine matrices in 3x4 storage
+#pragma unroll
     for (int r = 0; r < 3; r++) {
+#pragma unroll
         for (int c = 0; c < 4; c++) {
             double s = A[4 * r] * B[c] + A[4 * r + 1] * B[4 + c] + A[4 * r + 2] * B[8 + c];
             if (c == 3) s += A[4 * r + 3];
-            R[4 * r + c] = s;
+            C[4 * r + c] = s;
         }
     }
-    for (int i = 0; i < 12; i++) C[i] = R[i];
 }
 
 // Re-centre the raw sums (taken about `origin`) to the pair centroids, solve, compose.
-// Tinc: 3x4 row-major.  Returns 1 when a pivot was dropped.
-__device__ int solve_compose_dev(const double* S, const double* origin, double* Tinc, double* x, double* ratio_out) {
+// Tinc: 3x4 row-major.  Returns 1 when a pivot was dropped.  Every loop has compile-time bounds
+// and is fully unrolled so that the 6x6 system lives in registers (one thread runs this; with
+// run-time indexed arrays it spent ~25 us in local memory).
+__device__ __forceinline__ int solve_compose_dev(const double* __restrict__ S, const double (&origin)[3],
+                                                 double (&Tinc)[12], double (&x)[6], double& ratio_out) {
+#pragma unroll
     for (int i = 0; i < 12; i++) Tinc[i] = (i % 5 == 0) ? 1.0 : 0.0;
+#pragma unroll
     for (int i = 0; i < 6; i++) x[i] = 0.0;
-    *ratio_out = 0.0;
+    ratio_out = 0.0;
     const double cnt = S[36];
     if (cnt < 1.0) return 1;
     const double A[9] = {S[0], S[1], S[2], S[1], S[3], S[4], S[2], S[4], S[5]};
     double B[9];
+#pragma unroll
     for (int i = 0; i < 9; i++) B[i] = S[6 + i];
     const double C[9] = {S[15], S[16], S[17], S[16], S[18], S[19], S[17], S[19], S[20]};
+    const double icnt = 1.0 / cnt;
     double dp[3], dq[3], de[3], ep[3];
+#pragma unroll
     for (int k = 0; k < 3; k++) {
-        dp[k] = S[27 + k] / cnt;
-        dq[k] = S[30 + k] / cnt;
+        dp[k] = S[27 + k] * icnt;
+        dq[k] = S[30 + k] * icnt;
         de[k] = dp[k] + dq[k];
         ep[k] = dp[k] - dq[k];
     }
     // m = m' - K n with K = skew(de);  r = r' - ep.n
     const double K[9] = {0, -de[2], de[1], de[2], 0, -de[0], -de[1], de[0], 0};
     double BKt[9], KC[9], KCKt[9];
+#pragma unroll
     for (int r = 0; r < 3; r++)
+#pragma unroll
         for (int c = 0; c < 3; c++) {
-            double s1 = 0, s2 = 0;
-            for (int k = 0; k < 3; k++) { s1 += B[3 * r + k] * K[3 * c + k]; s2 += K[3 * r + k] * C[3 * k + c]; }
-            BKt[3 * r + c] = s1;
-            KC[3 * r + c] = s2;
+            BKt[3 * r + c] = B[3 * r] * K[3 * c] + B[3 * r + 1] * K[3 * c + 1] + B[3 * r + 2] * K[3 * c + 2];
+            KC[3 * r + c] = K[3 * r] * C[c] + K[3 * r + 1] * C[3 + c] + K[3 * r + 2] * C[6 + c];
         }
+#pragma unroll
     for (int r = 0; r < 3; r++)
-        for (int c = 0; c < 3; c++) {
-            double s = 0;
-            for (int k = 0; k < 3; k++) s += KC[3 * r + k] * K[3 * c + k];
-            KCKt[3 * r + c] = s;
-        }
+#pragma unroll
+        for (int c = 0; c < 3; c++)
+            KCKt[3 * r + c] = KC[3 * r] * K[3 * c] + KC[3 * r + 1] * K[3 * c + 1] + KC[3 * r + 2] * K[3 * c + 2];
     double H[36];
+#pragma unroll
     for (int r = 0; r < 3; r++)
+#pragma unroll
         for (int c = 0; c < 3; c++) {
-            double at = A[3 * r + c] - BKt[3 * r + c] - BKt[3 * c + r] + KCKt[3 * r + c];
-            double bt = B[3 * r + c] - KC[3 * r + c];
+            const double at = A[3 * r + c] - BKt[3 * r + c] - BKt[3 * c + r] + KCKt[3 * r + c];
+            const double bt = B[3 * r + c] - KC[3 * r + c];
             H[6 * r + c] = at;
             H[6 * r + 3 + c] = bt;
             H[6 * (3 + c) + r] = bt;
             H[6 * (3 + r) + 3 + c] = C[3 * r + c];
         }
     double Ce[3], Be[3];
+#pragma unroll
     for (int r = 0; r < 3; r++) {
         Ce[r] = C[3 * r] * ep[0] + C[3 * r + 1] * ep[1] + C[3 * r + 2] * ep[2];
         Be[r] = B[3 * r] * ep[0] + B[3 * r + 1] * ep[1] + B[3 * r + 2] * ep[2];
@@ -254,65 +264,80 @@ __device__ int solve_compose_dev(const double* S, const double* origin, double* 
     const double Kbn[3] = {de[1] * bn[2] - de[2] * bn[1], de[2] * bn[0] - de[0] * bn[2], de[0] * bn[1] - de[1] * bn[0]};
     const double KCe[3] = {de[1] * Ce[2] - de[2] * Ce[1], de[2] * Ce[0] - de[0] * Ce[2], de[0] * Ce[1] - de[1] * Ce[0]};
     double g[6];
+#pragma unroll
     for (int r = 0; r < 3; r++) {
         g[r] = S[21 + r] - Be[r] - Kbn[r] + KCe[r];
         g[3 + r] = bn[r] - Ce[r];
     }
-    // LDL^T with relative pivot guard: d_j <= 1e-6 * H_jj drops component j
-    double L[36], D[6];
-    int dead[6];
+    // LDL^T with relative pivot guard: d_j <= 1e-6 * H_jj drops component j.  A dropped pivot
+    // keeps D = 0 and a zero column in L, so the unguarded sums below simply skip it.
+    double L[36], D[6], iD[6];
+    bool dead[6];
+#pragma unroll
     for (int i = 0; i < 36; i++) L[i] = 0.0;
     int degenerate = 0;
     double minratio = 1.0;
+#pragma unroll
     for (int j = 0; j < 6; j++) {
         double d = H[6 * j + j];
-        for (int k = 0; k < j; k++)
-            if (!dead[k]) d -= L[6 * j + k] * L[6 * j + k] * D[k];
-        double ratio = H[6 * j + j] > 0 ? d / H[6 * j + j] : 0.0;
-        if (ratio < minratio) minratio = ratio;
-        dead[j] = 0;
-        if (!(d > 1e-6 * H[6 * j + j]) || !(H[6 * j + j] > 0)) { dead[j] = 1; degenerate = 1; D[j] = 0; continue; }
-        D[j] = d;
+#pragma unroll
+        for (int k = 0; k < j; k++) d -= L[6 * j + k] * L[6 * j + k] * D[k];
+        const double hjj = H[6 * j + j];
+        const double ratio = hjj > 0 ? d / hjj : 0.0;
+        minratio = ratio < minratio ? ratio : minratio;
+        dead[j] = !(d > 1e-6 * hjj) || !(hjj > 0);
+        degenerate |= dead[j] ? 1 : 0;
+        D[j] = dead[j] ? 0.0 : d;
+        iD[j] = dead[j] ? 0.0 : 1.0 / d;
+#pragma unroll
         for (int i = j + 1; i < 6; i++) {
             double vv = H[6 * i + j];
-            for (int k = 0; k < j; k++)
-                if (!dead[k]) vv -= L[6 * i + k] * L[6 * j + k] * D[k];
-            L[6 * i + j] = vv / d;
+#pragma unroll
+            for (int k = 0; k < j; k++) vv -= L[6 * i + k] * L[6 * j + k] * D[k];
+            L[6 * i + j] = vv * iD[j];
         }
     }
-    *ratio_out = minratio;
+    ratio_out = minratio;
     double y[6];
+#pragma unroll
     for (int i = 0; i < 6; i++) {
         double vv = -g[i];
-        for (int k = 0; k < i; k++)
-            if (!dead[k]) vv -= L[6 * i + k] * y[k];
+#pragma unroll
+        for (int k = 0; k < i; k++) vv -= L[6 * i + k] * y[k];
         y[i] = dead[i] ? 0.0 : vv;
     }
-    for (int i = 0; i < 6; i++) y[i] = dead[i] ? 0.0 : y[i] / D[i];
+#pragma unroll
+    for (int i = 0; i < 6; i++) y[i] = y[i] * iD[i];
+#pragma unroll
     for (int i = 5; i >= 0; i--) {
-        if (dead[i]) { x[i] = 0.0; continue; }
         double vv = y[i];
-        for (int k = i + 1; k < 6; k++)
-            if (!dead[k]) vv -= L[6 * k + i] * x[k];
-        x[i] = vv;
+#pragma unroll
+        for (int k = i + 1; k < 6; k++) vv -= L[6 * k + i] * x[k];
+        x[i] = dead[i] ? 0.0 : vv;
     }
     // Tinc = Tr(qbar) R Tr(t cos th) R Tr(-pbar):  x -> R(R(x - pbar) + t cos th) + qbar
     const double an = sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
     const double th = atan(an);
     double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    double sn, ct;
+    sincos(th, &sn, &ct);
     if (an > 1e-300) {
-        const double u[3] = {x[0] / an, x[1] / an, x[2] / an};
-        const double c = cos(th), s = sin(th), Cc = 1.0 - c;
-        R[0] = c + u[0] * u[0] * Cc;        R[1] = u[0] * u[1] * Cc - u[2] * s; R[2] = u[0] * u[2] * Cc + u[1] * s;
-        R[3] = u[1] * u[0] * Cc + u[2] * s; R[4] = c + u[1] * u[1] * Cc;        R[5] = u[1] * u[2] * Cc - u[0] * s;
-        R[6] = u[2] * u[0] * Cc - u[1] * s; R[7] = u[2] * u[1] * Cc + u[0] * s; R[8] = c + u[2] * u[2] * Cc;
+        const double ia = 1.0 / an;
+        const double u[3] = {x[0] * ia, x[1] * ia, x[2] * ia};
+        const double Cc = 1.0 - ct;
+        R[0] = ct + u[0] * u[0] * Cc;        R[1] = u[0] * u[1] * Cc - u[2] * sn; R[2] = u[0] * u[2] * Cc + u[1] * sn;
+        R[3] = u[1] * u[0] * Cc + u[2] * sn; R[4] = ct + u[1] * u[1] * Cc;        R[5] = u[1] * u[2] * Cc - u[0] * sn;
+        R[6] = u[2] * u[0] * Cc - u[1] * sn; R[7] = u[2] * u[1] * Cc + u[0] * sn; R[8] = ct + u[2] * u[2] * Cc;
     }
-    const double ct = cos(th);
     double pbar[3], qbar[3], tc[3];
+#pragma unroll
     for (int k = 0; k < 3; k++) { pbar[k] = origin[k] + dp[k]; qbar[k] = origin[k] + dq[k]; tc[k] = x[3 + k] * ct; }
     double R2[9];
+#pragma unroll
     for (int r = 0; r < 3; r++)
+#pragma unroll
         for (int c = 0; c < 3; c++) R2[3 * r + c] = R[3 * r] * R[c] + R[3 * r + 1] * R[3 + c] + R[3 * r + 2] * R[6 + c];
+#pragma unroll
     for (int r = 0; r < 3; r++) {
         Tinc[4 * r] = R2[3 * r]; Tinc[4 * r + 1] = R2[3 * r + 1]; Tinc[4 * r + 2] = R2[3 * r + 2];
         Tinc[4 * r + 3] = qbar[r] + (R[3 * r] * tc[0] + R[3 * r + 1] * tc[1] + R[3 * r + 2] * tc[2]) -
@@ -371,11 +396,14 @@ __global__ void __launch_bounds__(kSolveThreads) solve_kernel(const __grid_const
     st->prev_diff = diff;
     double Tinc[12], x[6], ratio;
     const double origin[3] = {st->origin[0], st->origin[1], st->origin[2]};
-    const int deg = solve_compose_dev(sS, origin, Tinc, x, &ratio);
+    const int deg = solve_compose_dev(sS, origin, Tinc, x, ratio);
     if (deg) st->degenerate = 1;
     if (ratio < st->min_ratio) st->min_ratio = ratio;
-    double Tn[12];
-    mat34_mul(Tinc, st->T, Tn);                                                                // myicp.cpp:138
+    double Told[12], Tn[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) Told[i] = st->T[i];
+    mat34_mul(Tinc, Told, Tn);                                                                 // myicp.cpp:138
+#pragma unroll
     for (int i = 0; i < 12; i++) { st->T[i] = Tn[i]; st->Tf[i] = (float)Tn[i]; }
     st->iter = st->iter + 1;
     st->pairs = (unsigned long long)(sS[36] + 0.5);
@@ -383,7 +411,8 @@ __global__ void __launch_bounds__(kSolveThreads) solve_kernel(const __grid_const
 
 __global__ void solve_compose_kernel(const double* in /*37 sums + 3 origin*/, double* out /*12 T + 6 x + ratio + deg*/) {
     double Tinc[12], x[6], ratio;
-    int deg = solve_compose_dev(in, in + ICP_NSUMS, Tinc, x, &ratio);
+    const double origin[3] = {in[ICP_NSUMS], in[ICP_NSUMS + 1], in[ICP_NSUMS + 2]};
+    int deg = solve_compose_dev(in, origin, Tinc, x, ratio);
     for (int i = 0; i < 12; i++) out[i] = Tinc[i];
     for (int i = 0; i < 6; i++) out[12 + i] = x[i];
     out[18] = ratio;
@@ -572,7 +601,7 @@ int icp_run_loop(icpsymm_ctx* ctx, int max_iters, float thr, const float* T_init
         key.max_iters = max_iters; key.nseg = nseg; key.blocks_per_seg = bps;
         key.src_pitch = S.shape.pitch; key.tgt_pitch = T.shape.pitch;
         key.p0 = S.pts; key.p1 = T.pts; key.p2 = ctx->partial; key.p3 = ctx->corr_pos; key.p4 = ctx->d_state;
-        key.p5 = ctx->opt_trace ? (const void*)ctx->trace_T : (const void*)T.boxes;
+        key.p5 = ctx->opt_trace ? (const void*)ctx->trace_T : (const void*)T.nodes;
         key.shard_rank = ctx->shard_rank; key.shard_world = ctx->shard_world; key.trace = ctx->opt_trace;
         // pointers of the remaining arrays change only together with the ones above (same reserve calls)
         if (!ctx->graph_exec || !(ctx->graph_key == key)) {

@@ -15,7 +15,7 @@ struct CloudSet {
     TreeShape shape{};
     float4* pts = nullptr;
     float4* nrm = nullptr;
-    Box* boxes = nullptr;
+    WideNode* nodes = nullptr;
     uint32_t* pos_of_orig = nullptr;
     uint32_t* counts = nullptr;   // device, nseg
     uint32_t* bbox = nullptr;     // device, nseg*8 ordered-uint (lo xyz, pad, hi xyz, pad) during build
@@ -27,7 +27,7 @@ struct CloudSet {
 
     CloudView view() const {
         CloudView v;
-        v.pts = pts; v.nrm = nrm; v.boxes = boxes; v.pos_of_orig = pos_of_orig; v.counts = counts;
+        v.pts = pts; v.nrm = nrm; v.nodes = nodes; v.pos_of_orig = pos_of_orig; v.counts = counts;
         v.shape = shape; v.nseg = nseg;
         return v;
     }

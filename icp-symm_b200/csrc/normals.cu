@@ -3,7 +3,7 @@
 // The reference calls pcl::NormalEstimation with setKSearch(10) (myicp.cpp:160) on each cloud:
 // kd-tree kNN, 3x3 covariance of the neighbourhood, eigenvector of the smallest eigenvalue,
 // flip towards the viewpoint (0,0,0), curvature = l0 / (l0+l1+l2).  Here one thread owns one
-// Morton-sorted point: exact kNN-k over the cloud's own box hierarchy (self included, ties by
+// Hilbert-sorted point: exact kNN-k over the cloud's own box hierarchy (self included, ties by
 // lowest original index), covariance about the neighbourhood mean taken relative to the query
 // point (so the fp32 subtractions are exact), cyclic-Jacobi eigen-decomposition in registers.
 #include <cfloat>
@@ -47,12 +47,12 @@ __global__ void __launch_bounds__(128) normals_kernel(const __grid_constant__ No
     const uint32_t cnt = P.cloud.counts[seg];
     if (i >= cnt) return;
     const float4* __restrict__ pts = P.cloud.pts + (size_t)seg * pitch;
-    const Box* __restrict__ boxes = P.cloud.boxes + (size_t)seg * P.cloud.shape.nodes_per_seg;
+    const WideNode* __restrict__ boxes = P.cloud.nodes + (size_t)seg * P.cloud.shape.nodes_per_seg;
     const uint32_t* __restrict__ pos_of_orig = P.cloud.pos_of_orig + (size_t)seg * pitch;
     const float4 q = ldg4(pts + i);
     const int k = P.k;
 
-    // first bound: the query's own leaf group and its Morton neighbours
+    // first bound: the query's own leaf group and its neighbours along the curve
     KList<KMAX> L;
     L.init();
     const uint32_t n_groups = pitch / ICP_LEAF;

@@ -1,16 +1,24 @@
-// search.cuh -- exact nearest-neighbour traversal of the implicit F-ary box hierarchy.
+// search.cuh -- exact nearest-neighbour traversal of the implicit 8-ary wide-node hierarchy.
 //
 // Replaces the correspondence search the reference leaves as a todo (ICP/myicp.cpp:128-131)
 // and the kd-tree PCL's NormalEstimation uses for its k=10 neighbourhoods (myicp.cpp:157-160).
 //
-// The hierarchy is implicit: node i of level l covers nodes [i*F, i*F+F) of level l-1, level 0
-// node g covers sorted points [g*LEAF, g*LEAF+LEAF).  Every level is padded to a multiple of F
-// with empty boxes (lo=+inf, hi=-inf, bound=+inf), so traversal needs no stack and no per-level
-// counts: "next node" is i+1, and when i+1 crosses a multiple of F the walk pops to the parent.
-// Candidates are ranked by (d2, original index) so ties go to the lowest original index, and a
-// subtree is skipped only when its bound is strictly greater than the current best d2.
+// The hierarchy is implicit: node i of level l covers nodes [8i, 8i+8) of level l-1, level 0
+// node g covers sorted points [8g, 8g+8).  One WideNode record holds the tight boxes of the 8
+// children of an internal node, so a visit is 12 independent 16-byte loads followed by 8 bound
+// tests, and the children that survive become an 8-bit pending mask.  The masks of all levels
+// live in one 64-bit register (one byte per level), so the walk needs no stack in memory:
+//   pop the lowest pending child of the current node; if it is a leaf group scan its 8 points,
+//   otherwise test its 8 children and make it the current node; when a mask runs empty go up.
+// Padding nodes carry empty boxes (lo=+inf, hi=-inf: bound=+inf) and are never entered.
+// Candidates are ranked by (d2, original index): ties go to the lowest original index, and a
+// subtree is skipped only when its bound is strictly greater than the current best d2.  The
+// bound uses the same separately rounded operations as the distance, so it can never exceed the
+// distance of a member point (monotone rounding): the search is exact, not approximate.
 #pragma once
 #include "common.cuh"
+
+#define ICP_INF_BITS 0x7f800000u
 
 struct Best {
     float d2;
@@ -19,7 +27,7 @@ struct Best {
 };
 
 __device__ __forceinline__ void best_init(Best& b) {
-    b.d2 = __int_as_float(0x7f800000);
+    b.d2 = __uint_as_float(ICP_INF_BITS);
     b.id = ICP_INVALID_ID;
     b.pos = 0xffffffffu;
 }
@@ -40,45 +48,100 @@ __device__ __forceinline__ void scan_leaf(const float4* __restrict__ seg_pts, ui
     for (int j = 0; j < ICP_LEAF; j++) best_offer(b, c[j], g * ICP_LEAF + j, qx, qy, qz);
 }
 
-// descend to the leaf whose chain of boxes is nearest at every level: a cheap first bound
-__device__ __forceinline__ void greedy_descent(const TreeShape& sh, const Box* __restrict__ seg_boxes,
-                                               const float4* __restrict__ seg_pts, float qx, float qy, float qz,
-                                               Best& b) {
-    uint32_t node = 0;
-    for (int l = (int)sh.n_levels - 1; l > 0; --l) {
-        const Box* cb = seg_boxes + sh.level_off[l - 1] + node * ICP_FAN;
-        float blb = __int_as_float(0x7f800000);
-        uint32_t bc = 0;
+// bounds (as ordered bit patterns; every bound is >= +0) of the 8 children stored in one record
+__device__ __forceinline__ void child_bounds(const WideNode* __restrict__ nd, float qx, float qy, float qz,
+                                             uint32_t lbb[ICP_FAN]) {
+    const float4* p = reinterpret_cast<const float4*>(nd);
+    float4 r[12];
 #pragma unroll
-        for (int c = 0; c < ICP_FAN; c++) {
-            float4 lo = ldg4(&cb[c].lo), hi = ldg4(&cb[c].hi);
-            float lb = box_dist2_rn(lo, hi, qx, qy, qz);
-            if (lb < blb) { blb = lb; bc = c; }
+    for (int j = 0; j < 12; j++) r[j] = ldg4(p + j);
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const float lox[4] = {r[h].x, r[h].y, r[h].z, r[h].w};
+        const float loy[4] = {r[2 + h].x, r[2 + h].y, r[2 + h].z, r[2 + h].w};
+        const float loz[4] = {r[4 + h].x, r[4 + h].y, r[4 + h].z, r[4 + h].w};
+        const float hix[4] = {r[6 + h].x, r[6 + h].y, r[6 + h].z, r[6 + h].w};
+        const float hiy[4] = {r[8 + h].x, r[8 + h].y, r[8 + h].z, r[8 + h].w};
+        const float hiz[4] = {r[10 + h].x, r[10 + h].y, r[10 + h].z, r[10 + h].w};
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            float ex = fmaxf(fmaxf(__fsub_rn(lox[c], qx), __fsub_rn(qx, hix[c])), 0.f);
+            float ey = fmaxf(fmaxf(__fsub_rn(loy[c], qy), __fsub_rn(qy, hiy[c])), 0.f);
+            float ez = fmaxf(fmaxf(__fsub_rn(loz[c], qz), __fsub_rn(qz, hiz[c])), 0.f);
+            lbb[4 * h + c] =
+                __float_as_uint(__fadd_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)), __fmul_rn(ez, ez)));
         }
-        node = node * ICP_FAN + bc;
     }
-    scan_leaf(seg_pts, node, qx, qy, qz, b);
 }
 
-// full exact search; `b` may already hold a candidate (warm start / greedy descent)
-__device__ __forceinline__ void nn_traverse(const TreeShape& sh, const Box* __restrict__ seg_boxes,
+// pending mask of the children whose bound does not exceed `bound_bits`, plus the nearest of them
+// (pref, valid when the mask is non-zero): the walk enters the nearest child first so that the
+// bound tightens as early as possible, the others follow in index order.
+__device__ __forceinline__ uint32_t child_mask(const WideNode* __restrict__ nd, float qx, float qy, float qz,
+                                               uint32_t bound_bits, int& pref) {
+    uint32_t lbb[ICP_FAN];
+    child_bounds(nd, qx, qy, qz, lbb);
+    uint32_t m = 0, kmin = 0xffffffffu;
+#pragma unroll
+    for (int c = 0; c < ICP_FAN; c++) {
+        m |= (lbb[c] <= bound_bits && lbb[c] != ICP_INF_BITS) ? (1u << c) : 0u;
+        kmin = min(kmin, (lbb[c] & ~7u) | (uint32_t)c);   // child index rides in the 3 low mantissa bits
+    }
+    pref = (int)(kmin & 7u);
+    return m;
+}
+
+// Generic exact walk.  V supplies bound_bits() (current pruning bound, ordered bits) and
+// leaf(g) (offer the 8 points of leaf group g).
+template <typename V>
+__device__ __forceinline__ void wide_traverse(const TreeShape& sh, const WideNode* __restrict__ seg_nodes,
+                                              float qx, float qy, float qz, V& v) {
+    const int top = (int)sh.n_levels - 1;
+    if (top == 0) { v.leaf(0); return; }       // a single leaf group, no internal node
+    int l = top, pref;
+    uint32_t i = 0;
+    unsigned long long masks =
+        (unsigned long long)child_mask(seg_nodes + sh.level_off[top], qx, qy, qz, v.bound_bits(), pref) << (8 * (top - 1));
+    for (;;) {
+        const int sh8 = 8 * (l - 1);
+        const uint32_t m = (uint32_t)(masks >> sh8) & 0xffu;
+        if (m == 0) {
+            if (l == top) break;
+            ++l; i >>= ICP_LOG_FAN;
+            pref = -1;
+            continue;
+        }
+        // first pop after a node was opened: its nearest child if it is pending (the index rides in
+        // the low bound bits, so a near-tie may name a child that just missed the mask); afterwards
+        // lowest index first
+        const int c = (pref >= 0 && ((m >> pref) & 1u)) ? pref : (__ffs((int)m) - 1);
+        pref = -1;
+        masks &= ~(1ull << (sh8 + c));
+        const uint32_t child = (i << ICP_LOG_FAN) + (uint32_t)c;
+        if (l == 1) {
+            v.leaf(child);
+        } else {
+            --l; i = child;
+            const uint32_t cm = child_mask(seg_nodes + sh.level_off[l] + i, qx, qy, qz, v.bound_bits(), pref);
+            masks |= (unsigned long long)cm << (8 * (l - 1));   // that byte is empty: its node was exhausted
+        }
+    }
+}
+
+struct NNVisitor {
+    Best& b;
+    const float4* __restrict__ pts;
+    float qx, qy, qz;
+    __device__ __forceinline__ uint32_t bound_bits() const { return __float_as_uint(b.d2); }
+    __device__ __forceinline__ void leaf(uint32_t g) { scan_leaf(pts, g, qx, qy, qz, b); }
+};
+
+// full exact 1-NN search; `b` may already hold a candidate (warm start / greedy descent)
+__device__ __forceinline__ void nn_traverse(const TreeShape& sh, const WideNode* __restrict__ seg_nodes,
                                             const float4* __restrict__ seg_pts, float qx, float qy, float qz,
                                             Best& b) {
-    const int top = (int)sh.n_levels - 1;
-    int l = top;
-    uint32_t i = 0;
-    for (;;) {
-        const Box* nb = seg_boxes + sh.level_off[l] + i;
-        float4 lo = ldg4(&nb->lo), hi = ldg4(&nb->hi);
-        float lb = box_dist2_rn(lo, hi, qx, qy, qz);
-        if (lb <= b.d2 && lb < __int_as_float(0x7f800000)) {  // empty (padding) boxes have bound +inf
-            if (l > 0) { --l; i <<= ICP_LOG_FAN; continue; }
-            scan_leaf(seg_pts, i, qx, qy, qz, b);
-        }
-        ++i;
-        while (l < top && (i & (ICP_FAN - 1)) == 0) { i >>= ICP_LOG_FAN; ++l; }
-        if (l == top) break;
-    }
+    NNVisitor v{b, seg_pts, qx, qy, qz};
+    wide_traverse(sh, seg_nodes, qx, qy, qz, v);
 }
 
 // ---- k nearest: ascending list of keys (d2 bits << 32 | original index), k <= KMAX at run time ----
@@ -120,34 +183,35 @@ struct KList {
     __device__ __forceinline__ uint32_t bound_bits() const { return (uint32_t)(kth >> 32); }
 };
 
-// exact k nearest of (qx,qy,qz) inside one segment.  Leaves [g_lo, g_hi] were already offered by
-// the caller (the query's own Morton neighbourhood, which gives a finite first bound) and are
-// skipped here so that no candidate enters the list twice.  Sentinel padding points are ignored.
+// Leaves [g_lo, g_hi] were already offered by the caller (the query's own neighbourhood along the curve,
+// which gives a finite first bound) and are skipped so that no candidate enters the list twice.
+// Sentinel padding points are ignored.
 template <int KMAX>
-__device__ __forceinline__ void knn_traverse(const TreeShape& sh, const Box* __restrict__ seg_boxes,
+struct KnnVisitor {
+    KList<KMAX>& L;
+    const float4* __restrict__ pts;
+    float qx, qy, qz;
+    int k;
+    uint32_t g_lo, g_hi;
+    __device__ __forceinline__ uint32_t bound_bits() const { return L.bound_bits(); }
+    __device__ __forceinline__ void leaf(uint32_t g) {
+        if (g >= g_lo && g <= g_hi) return;
+        const float4* lp = pts + (size_t)g * ICP_LEAF;
+        float4 c[ICP_LEAF];
+#pragma unroll
+        for (int j = 0; j < ICP_LEAF; j++) c[j] = ldg4(lp + j);
+#pragma unroll
+        for (int j = 0; j < ICP_LEAF; j++) {
+            uint32_t id = __float_as_uint(c[j].w);
+            if (id != (uint32_t)ICP_INVALID_ID) L.offer(k, dist2_rn(qx, qy, qz, c[j].x, c[j].y, c[j].z), id);
+        }
+    }
+};
+
+template <int KMAX>
+__device__ __forceinline__ void knn_traverse(const TreeShape& sh, const WideNode* __restrict__ seg_nodes,
                                              const float4* __restrict__ seg_pts, float qx, float qy, float qz,
                                              int k, uint32_t g_lo, uint32_t g_hi, KList<KMAX>& L) {
-    const int top = (int)sh.n_levels - 1;
-    int l = top;
-    uint32_t i = 0;
-    for (;;) {
-        const Box* nb = seg_boxes + sh.level_off[l] + i;
-        float4 lo = ldg4(&nb->lo), hi = ldg4(&nb->hi);
-        uint32_t lbb = __float_as_uint(box_dist2_rn(lo, hi, qx, qy, qz));
-        if (lbb <= L.bound_bits() && lbb != 0x7f800000u) {
-            if (l > 0) { --l; i <<= ICP_LOG_FAN; continue; }
-            if (i < g_lo || i > g_hi) {
-                const float4* lp = seg_pts + (size_t)i * ICP_LEAF;
-#pragma unroll
-                for (int j = 0; j < ICP_LEAF; j++) {
-                    float4 c = ldg4(lp + j);
-                    uint32_t id = __float_as_uint(c.w);
-                    if (id != ICP_INVALID_ID) L.offer(k, dist2_rn(qx, qy, qz, c.x, c.y, c.z), id);
-                }
-            }
-        }
-        ++i;
-        while (l < top && (i & (ICP_FAN - 1)) == 0) { i >>= ICP_LOG_FAN; ++l; }
-        if (l == top) break;
-    }
+    KnnVisitor<KMAX> v{L, seg_pts, qx, qy, qz, k, g_lo, g_hi};
+    wide_traverse(sh, seg_nodes, qx, qy, qz, v);
 }
