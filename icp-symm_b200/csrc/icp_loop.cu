@@ -121,19 +121,24 @@ __global__ void __launch_bounds__(kNNThreads) nn_accum_kernel(const __grid_const
         float v[ICP_NSUMS];
 #pragma unroll
         for (int k = 0; k < ICP_NSUMS; k++) v[k] = 0.f;
-        if (i < qhi && nt > 0) {
+        const bool active = i < qhi && nt > 0;
+        float3 p = make_float3(0.f, 0.f, 0.f);
+        Best b;
+        best_init(b);
+        if (active) {
             const float4 s = ldg4(spts + i);
-            const float3 p = apply_rn(sT, s.x, s.y, s.z);
-            Best b;
-            best_init(b);
+            p = apply_rn(sT, s.x, s.y, s.z);
             if (lp.identity_pairs) {
                 uint32_t pos = P.tgt.pos_of_orig[(size_t)seg * P.tgt.shape.pitch + __float_as_uint(s.w)];
                 best_offer(b, ldg4(tpts + pos), pos, p.x, p.y, p.z);
             } else {
                 uint32_t prev = lp.warm_start ? corr[i] : 0xffffffffu;
                 if (prev < nt) best_offer(b, ldg4(tpts + prev), prev, p.x, p.y, p.z);
-                nn_traverse(P.tgt.shape, tbox, tpts, p.x, p.y, p.z, b);
             }
+        }
+        // warp-synchronous exact search: the 32 lanes are 32 neighbouring source points
+        if (!lp.identity_pairs && nt > 0) nn_traverse_warp(P.tgt.shape, tbox, tpts, p.x, p.y, p.z, active, b);
+        if (active) {
             corr[i] = b.pos;
             if (b.pos < nt) {
                 const float4 q = ldg4(tpts + b.pos);

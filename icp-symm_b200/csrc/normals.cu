@@ -40,34 +40,39 @@ __device__ __forceinline__ void jacobi_rotate(float& app, float& aqq, float& apq
 
 template <int KMAX>
 __global__ void __launch_bounds__(128) normals_kernel(const __grid_constant__ NormalParams P) {
+    // one block = 128 consecutive sorted points of ONE segment, so that a warp never straddles two
+    // clouds and its 32 lanes can walk the hierarchy together
     const uint32_t pitch = P.cloud.shape.pitch;
-    size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= (size_t)P.cloud.nseg * pitch) return;
-    const uint32_t seg = (uint32_t)(j / pitch), i = (uint32_t)(j - (size_t)seg * pitch);
+    const uint32_t chunks = (pitch + 127u) / 128u;
+    const uint32_t seg = blockIdx.x / chunks, i = (blockIdx.x - seg * chunks) * 128u + threadIdx.x;
+    const size_t j = (size_t)seg * pitch + i;
     const uint32_t cnt = P.cloud.counts[seg];
-    if (i >= cnt) return;
+    const bool active = i < cnt;
     const float4* __restrict__ pts = P.cloud.pts + (size_t)seg * pitch;
     const WideNode* __restrict__ boxes = P.cloud.nodes + (size_t)seg * P.cloud.shape.nodes_per_seg;
     const uint32_t* __restrict__ pos_of_orig = P.cloud.pos_of_orig + (size_t)seg * pitch;
-    const float4 q = ldg4(pts + i);
+    const float4 q = active ? ldg4(pts + i) : make_float4(0.f, 0.f, 0.f, 0.f);
     const int k = P.k;
 
     // first bound: the query's own leaf group and its neighbours along the curve
     KList<KMAX> L;
     L.init();
     const uint32_t n_groups = pitch / ICP_LEAF;
-    const uint32_t g = i / ICP_LEAF, w = (k <= 16) ? 1u : 2u;
+    const uint32_t g = active ? i / ICP_LEAF : 0u, w = (k <= 16) ? 1u : 2u;
     const uint32_t g_lo = g >= w ? g - w : 0u, g_hi = (g + w < n_groups) ? g + w : n_groups - 1;
-    for (uint32_t gg = g_lo; gg <= g_hi; gg++) {
-        const float4* lp = pts + (size_t)gg * ICP_LEAF;
+    if (active) {
+        for (uint32_t gg = g_lo; gg <= g_hi; gg++) {
+            const float4* lp = pts + (size_t)gg * ICP_LEAF;
 #pragma unroll
-        for (int t = 0; t < ICP_LEAF; t++) {
-            float4 c = ldg4(lp + t);
-            uint32_t id = __float_as_uint(c.w);
-            if (id != (uint32_t)ICP_INVALID_ID) L.offer(k, dist2_rn(q.x, q.y, q.z, c.x, c.y, c.z), id);
+            for (int t = 0; t < ICP_LEAF; t++) {
+                float4 c = ldg4(lp + t);
+                uint32_t id = __float_as_uint(c.w);
+                if (id != (uint32_t)ICP_INVALID_ID) L.offer(k, dist2_rn(q.x, q.y, q.z, c.x, c.y, c.z), id);
+            }
         }
     }
-    knn_traverse<KMAX>(P.cloud.shape, boxes, pts, q.x, q.y, q.z, k, g_lo, g_hi, L);
+    knn_traverse_warp<KMAX>(P.cloud.shape, boxes, pts, q.x, q.y, q.z, k, g_lo, g_hi, active, L);
+    if (!active) return;
 
     // covariance of the neighbourhood, coordinates relative to the query point
     float ux[KMAX], uy[KMAX], uz[KMAX];
@@ -159,7 +164,7 @@ int icp_estimate_normals(icpsymm_ctx* ctx, CloudSet& cs, int k, const float vp[3
     P.vp[0] = vp ? vp[0] : 0.f; P.vp[1] = vp ? vp[1] : 0.f; P.vp[2] = vp ? vp[2] : 0.f;
     P.k = k;
     size_t slots = (size_t)cs.nseg * cs.shape.pitch;
-    uint32_t grid = (uint32_t)((slots + 127) / 128);
+    uint32_t grid = cs.nseg * ((cs.shape.pitch + 127u) / 128u);
     ICP_CUDA_CHECK(cudaMemsetAsync(cs.nrm, 0, slots * sizeof(float4), ctx->stream));
     if (k <= 10) normals_kernel<10><<<grid, 128, 0, ctx->stream>>>(P);
     else if (k <= 16) normals_kernel<16><<<grid, 128, 0, ctx->stream>>>(P);

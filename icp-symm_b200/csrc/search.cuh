@@ -91,6 +91,66 @@ __device__ __forceinline__ uint32_t child_mask(const WideNode* __restrict__ nd, 
     return m;
 }
 
+// Warp-synchronous variant: the 32 lanes hold 32 neighbouring queries (consecutive points of the
+// Hilbert-sorted source, a compact patch after any rigid transform) and walk the hierarchy
+// TOGETHER.  Every lane tests the same record against its own query and its own bound; a child
+// stays pending when ANY lane still needs it (one REDUX.OR), the nearest child over all lanes is
+// entered first (one REDUX.MIN).  Node records and leaf points are then warp-uniform loads, and
+// there is no divergence: the warp pays for the union of the 32 search regions once instead of
+// for 32 diverging walks.
+__device__ __forceinline__ uint32_t warp_child_mask(const WideNode* __restrict__ nd, float qx, float qy, float qz,
+                                                    uint32_t bound_bits, bool active, int& pref) {
+    uint32_t lbb[ICP_FAN];
+    child_bounds(nd, qx, qy, qz, lbb);
+    uint32_t m = 0, kmin = 0xffffffffu;
+#pragma unroll
+    for (int c = 0; c < ICP_FAN; c++) {
+        const bool pass = lbb[c] <= bound_bits && lbb[c] != ICP_INF_BITS;
+        m |= pass ? (1u << c) : 0u;
+        kmin = min(kmin, pass ? ((lbb[c] & ~7u) | (uint32_t)c) : 0xffffffffu);
+    }
+    m = active ? m : 0u;
+    kmin = active ? kmin : 0xffffffffu;
+    m = __reduce_or_sync(0xffffffffu, m);
+    kmin = __reduce_min_sync(0xffffffffu, kmin);
+    pref = (int)(kmin & 7u);   // only used when m != 0, i.e. when some lane passed a child
+    return m;
+}
+
+template <typename V>
+__device__ __forceinline__ void wide_traverse_warp(const TreeShape& sh, const WideNode* __restrict__ seg_nodes,
+                                                   float qx, float qy, float qz, bool active, V& v) {
+    const int top = (int)sh.n_levels - 1;
+    if (top == 0) { v.leaf(0); return; }
+    int l = top, pref;
+    uint32_t i = 0;
+    unsigned long long masks =
+        (unsigned long long)warp_child_mask(seg_nodes + sh.level_off[top], qx, qy, qz, v.bound_bits(), active, pref)
+        << (8 * (top - 1));
+    for (;;) {
+        const int sh8 = 8 * (l - 1);
+        const uint32_t m = (uint32_t)(masks >> sh8) & 0xffu;
+        if (m == 0) {
+            if (l == top) break;
+            ++l; i >>= ICP_LOG_FAN;
+            pref = -1;
+            continue;
+        }
+        const int c = (pref >= 0 && ((m >> pref) & 1u)) ? pref : (__ffs((int)m) - 1);
+        pref = -1;
+        masks &= ~(1ull << (sh8 + c));
+        const uint32_t child = (i << ICP_LOG_FAN) + (uint32_t)c;
+        if (l == 1) {
+            v.leaf(child);
+        } else {
+            --l; i = child;
+            const uint32_t cm =
+                warp_child_mask(seg_nodes + sh.level_off[l] + i, qx, qy, qz, v.bound_bits(), active, pref);
+            masks |= (unsigned long long)cm << (8 * (l - 1));
+        }
+    }
+}
+
 // Generic exact walk.  V supplies bound_bits() (current pruning bound, ordered bits) and
 // leaf(g) (offer the 8 points of leaf group g).
 template <typename V>
@@ -136,7 +196,16 @@ struct NNVisitor {
     __device__ __forceinline__ void leaf(uint32_t g) { scan_leaf(pts, g, qx, qy, qz, b); }
 };
 
-// full exact 1-NN search; `b` may already hold a candidate (warm start / greedy descent)
+// full exact 1-NN search of all lanes of a warp; each `b` may already hold a candidate (warm start).
+// Must be called by all 32 lanes; lanes without a query pass active = false.
+__device__ __forceinline__ void nn_traverse_warp(const TreeShape& sh, const WideNode* __restrict__ seg_nodes,
+                                                 const float4* __restrict__ seg_pts, float qx, float qy, float qz,
+                                                 bool active, Best& b) {
+    NNVisitor v{b, seg_pts, qx, qy, qz};
+    wide_traverse_warp(sh, seg_nodes, qx, qy, qz, active, v);
+}
+
+// per-thread variant (independent walks)
 __device__ __forceinline__ void nn_traverse(const TreeShape& sh, const WideNode* __restrict__ seg_nodes,
                                             const float4* __restrict__ seg_pts, float qx, float qy, float qz,
                                             Best& b) {
@@ -207,6 +276,14 @@ struct KnnVisitor {
         }
     }
 };
+
+template <int KMAX>
+__device__ __forceinline__ void knn_traverse_warp(const TreeShape& sh, const WideNode* __restrict__ seg_nodes,
+                                                  const float4* __restrict__ seg_pts, float qx, float qy, float qz,
+                                                  int k, uint32_t g_lo, uint32_t g_hi, bool active, KList<KMAX>& L) {
+    KnnVisitor<KMAX> v{L, seg_pts, qx, qy, qz, k, g_lo, g_hi};
+    wide_traverse_warp(sh, seg_nodes, qx, qy, qz, active, v);
+}
 
 template <int KMAX>
 __device__ __forceinline__ void knn_traverse(const TreeShape& sh, const WideNode* __restrict__ seg_nodes,
