@@ -85,7 +85,7 @@ __global__ void init_state_kernel(SegState* state, uint32_t nseg, InitArgs a, co
 // ------------------------------------------------------------------------------------------------
 // K1: search + accumulate
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kNNThreads) nn_accum_kernel(const __grid_constant__ NNParams P) {
+__global__ void __launch_bounds__(kNNThreads, 4) nn_accum_kernel(const __grid_constant__ NNParams P) {
     const uint32_t seg = blockIdx.x / P.blocks_per_seg;
     const uint32_t blk = blockIdx.x - seg * P.blocks_per_seg;
     const SegState* st = P.state + seg;
@@ -118,9 +118,6 @@ __global__ void __launch_bounds__(kNNThreads) nn_accum_kernel(const __grid_const
 
     for (uint32_t tile = blk; tile < ntiles; tile += P.blocks_per_seg) {
         const uint32_t i = qlo + tile * kNNThreads + tid;
-        float v[ICP_NSUMS];
-#pragma unroll
-        for (int k = 0; k < ICP_NSUMS; k++) v[k] = 0.f;
         const bool active = i < qhi && nt > 0;
         float3 p = make_float3(0.f, 0.f, 0.f);
         Best b;
@@ -138,6 +135,9 @@ __global__ void __launch_bounds__(kNNThreads) nn_accum_kernel(const __grid_const
         }
         // warp-synchronous exact search: the 32 lanes are 32 neighbouring source points
         if (!lp.identity_pairs && nt > 0) nn_traverse_warp(P.tgt.shape, tbox, tpts, p.x, p.y, p.z, active, b);
+        float v[ICP_NSUMS];   // declared after the walk so that none of it is live across it
+#pragma unroll
+        for (int k = 0; k < ICP_NSUMS; k++) v[k] = 0.f;
         if (active) {
             corr[i] = b.pos;
             if (b.pos < nt) {

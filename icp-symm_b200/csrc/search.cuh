@@ -5,11 +5,11 @@
 //
 // The hierarchy is implicit: node i of level l covers nodes [8i, 8i+8) of level l-1, level 0
 // node g covers sorted points [8g, 8g+8).  One WideNode record holds the tight boxes of the 8
-// children of an internal node, so a visit is 12 independent 16-byte loads followed by 8 bound
-// tests, and the children that survive become an 8-bit pending mask.  The masks of all levels
-// live in one 64-bit register (one byte per level), so the walk needs no stack in memory:
-//   pop the lowest pending child of the current node; if it is a leaf group scan its 8 points,
-//   otherwise test its 8 children and make it the current node; when a mask runs empty go up.
+// children of an internal node.  The pending children of every open level are an 8-bit mask and
+// the masks of all levels live in one 64-bit register, so the walk needs no stack in memory:
+//   pop a pending child of the current node (nearest first, then lowest index); if it is a leaf
+//   group scan its 8 points, otherwise test its 8 children and make it the current node; when a
+//   mask runs empty go up (parent index = i >> 3).
 // Padding nodes carry empty boxes (lo=+inf, hi=-inf: bound=+inf) and are never entered.
 // Candidates are ranked by (d2, original index): ties go to the lowest original index, and a
 // subtree is skipped only when its bound is strictly greater than the current best d2.  The
@@ -48,73 +48,77 @@ __device__ __forceinline__ void scan_leaf(const float4* __restrict__ seg_pts, ui
     for (int j = 0; j < ICP_LEAF; j++) best_offer(b, c[j], g * ICP_LEAF + j, qx, qy, qz);
 }
 
-// bounds (as ordered bit patterns; every bound is >= +0) of the 8 children stored in one record
-__device__ __forceinline__ void child_bounds(const WideNode* __restrict__ nd, float qx, float qy, float qz,
-                                             uint32_t lbb[ICP_FAN]) {
-    const float4* p = reinterpret_cast<const float4*>(nd);
-    float4 r[12];
-#pragma unroll
-    for (int j = 0; j < 12; j++) r[j] = ldg4(p + j);
-#pragma unroll
-    for (int h = 0; h < 2; h++) {
-        const float lox[4] = {r[h].x, r[h].y, r[h].z, r[h].w};
-        const float loy[4] = {r[2 + h].x, r[2 + h].y, r[2 + h].z, r[2 + h].w};
-        const float loz[4] = {r[4 + h].x, r[4 + h].y, r[4 + h].z, r[4 + h].w};
-        const float hix[4] = {r[6 + h].x, r[6 + h].y, r[6 + h].z, r[6 + h].w};
-        const float hiy[4] = {r[8 + h].x, r[8 + h].y, r[8 + h].z, r[8 + h].w};
-        const float hiz[4] = {r[10 + h].x, r[10 + h].y, r[10 + h].z, r[10 + h].w};
-#pragma unroll
-        for (int c = 0; c < 4; c++) {
-            float ex = fmaxf(fmaxf(__fsub_rn(lox[c], qx), __fsub_rn(qx, hix[c])), 0.f);
-            float ey = fmaxf(fmaxf(__fsub_rn(loy[c], qy), __fsub_rn(qy, hiy[c])), 0.f);
-            float ez = fmaxf(fmaxf(__fsub_rn(loz[c], qz), __fsub_rn(qz, hiz[c])), 0.f);
-            lbb[4 * h + c] =
-                __float_as_uint(__fadd_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)), __fmul_rn(ez, ez)));
-        }
-    }
-}
-
-// pending mask of the children whose bound does not exceed `bound_bits`, plus the nearest of them
-// (pref, valid when the mask is non-zero): the walk enters the nearest child first so that the
-// bound tightens as early as possible, the others follow in index order.
-__device__ __forceinline__ uint32_t child_mask(const WideNode* __restrict__ nd, float qx, float qy, float qz,
-                                               uint32_t bound_bits, int& pref) {
-    uint32_t lbb[ICP_FAN];
-    child_bounds(nd, qx, qy, qz, lbb);
-    uint32_t m = 0, kmin = 0xffffffffu;
-#pragma unroll
-    for (int c = 0; c < ICP_FAN; c++) {
-        m |= (lbb[c] <= bound_bits && lbb[c] != ICP_INF_BITS) ? (1u << c) : 0u;
-        kmin = min(kmin, (lbb[c] & ~7u) | (uint32_t)c);   // child index rides in the 3 low mantissa bits
-    }
-    pref = (int)(kmin & 7u);
-    return m;
-}
-
 // Warp-synchronous variant: the 32 lanes hold 32 neighbouring queries (consecutive points of the
 // Hilbert-sorted source, a compact patch after any rigid transform) and walk the hierarchy
-// TOGETHER.  Every lane tests the same record against its own query and its own bound; a child
-// stays pending when ANY lane still needs it (one REDUX.OR), the nearest child over all lanes is
-// entered first (one REDUX.MIN).  Node records and leaf points are then warp-uniform loads, and
-// there is no divergence: the warp pays for the union of the 32 search regions once instead of
-// for 32 diverging walks.
-__device__ __forceinline__ uint32_t warp_child_mask(const WideNode* __restrict__ nd, float qx, float qy, float qz,
-                                                    uint32_t bound_bits, bool active, int& pref) {
-    uint32_t lbb[ICP_FAN];
-    child_bounds(nd, qx, qy, qz, lbb);
-    uint32_t m = 0, kmin = 0xffffffffu;
-#pragma unroll
-    for (int c = 0; c < ICP_FAN; c++) {
-        const bool pass = lbb[c] <= bound_bits && lbb[c] != ICP_INF_BITS;
-        m |= pass ? (1u << c) : 0u;
-        kmin = min(kmin, pass ? ((lbb[c] & ~7u) | (uint32_t)c) : 0xffffffffu);
+// TOGETHER, so node records and leaf points are warp-uniform loads and nothing diverges: the warp
+// pays once for the union of the 32 search regions instead of for 32 diverging walks.
+//
+// A node visit is two-stage.  Stage 1: lane c (mod 8) tests child c against the bounding box of
+// the whole patch and the largest bound of any lane -- one box-box test per lane, and a
+// conservative superset because every step of the fp32 bound is monotone.  Stage 2: only the
+// children that survive are tested exactly, every lane against its own query and its own bound
+// (box broadcast by shuffles); a child stays pending when ANY lane still needs it.  Near
+// convergence one or two children survive stage 1, which halves the cost of a visit.
+//
+// Pending masks are computed under the bounds of that moment.  When a leaf scan improves a bound
+// the masks of all open levels become stale; a stale child is re-tested exactly (one box per lane)
+// when it is popped, before paying for a full visit.
+struct WarpPatch {
+    float lox, loy, loz, hix, hiy, hiz;  // bounding box of the active lanes' queries (warp-uniform)
+};
+
+__device__ __forceinline__ float warp_min_f(float x) {
+    return ordered_to_float(__reduce_min_sync(0xffffffffu, float_to_ordered(x)));
+}
+__device__ __forceinline__ float warp_max_f(float x) {
+    return ordered_to_float(__reduce_max_sync(0xffffffffu, float_to_ordered(x)));
+}
+
+__device__ __forceinline__ uint32_t point_box_bits(float lx, float ly, float lz, float hx, float hy, float hz,
+                                                   float qx, float qy, float qz) {
+    float ex = fmaxf(fmaxf(__fsub_rn(lx, qx), __fsub_rn(qx, hx)), 0.f);
+    float ey = fmaxf(fmaxf(__fsub_rn(ly, qy), __fsub_rn(qy, hy)), 0.f);
+    float ez = fmaxf(fmaxf(__fsub_rn(lz, qz), __fsub_rn(qz, hz)), 0.f);
+    return __float_as_uint(__fadd_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)), __fmul_rn(ez, ez)));
+}
+
+__device__ __forceinline__ uint32_t warp_node_test(const WideNode* __restrict__ nd, float qx, float qy, float qz,
+                                                   uint32_t my_bound, bool active, const WarpPatch& pb,
+                                                   uint32_t max_bound, int& pref) {
+    const int cl = threadIdx.x & 7;
+    const float* f = reinterpret_cast<const float*>(nd);
+    const float blx = __ldg(f + cl), bly = __ldg(f + 8 + cl), blz = __ldg(f + 16 + cl);
+    const float bhx = __ldg(f + 24 + cl), bhy = __ldg(f + 32 + cl), bhz = __ldg(f + 40 + cl);
+    // stage 1: box(patch) vs box(child cl).  For every query q of the patch lo-q >= lo-patch.hi and
+    // q-hi >= patch.lo-hi, and rounding is monotone, so this bound never exceeds a lane's own bound.
+    float ex = fmaxf(fmaxf(__fsub_rn(blx, pb.hix), __fsub_rn(pb.lox, bhx)), 0.f);
+    float ey = fmaxf(fmaxf(__fsub_rn(bly, pb.hiy), __fsub_rn(pb.loy, bhy)), 0.f);
+    float ez = fmaxf(fmaxf(__fsub_rn(blz, pb.hiz), __fsub_rn(pb.loz, bhz)), 0.f);
+    const uint32_t lbp = __float_as_uint(__fadd_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)), __fmul_rn(ez, ez)));
+    const bool pass1 = lbp <= max_bound && lbp != ICP_INF_BITS;
+    const uint32_t mask1 = __ballot_sync(0xffffffffu, pass1) & 0xffu;
+    const uint32_t kmin = __reduce_min_sync(0xffffffffu, pass1 ? ((lbp & ~7u) | (uint32_t)cl) : 0xffffffffu);
+    pref = (int)(kmin & 7u);
+    // stage 2: exact, per lane, only for the survivors
+    uint32_t mask2 = 0;
+    for (uint32_t mm = mask1; mm; mm &= mm - 1) {
+        const int c = __ffs((int)mm) - 1;
+        const float lx = __shfl_sync(0xffffffffu, blx, c), ly = __shfl_sync(0xffffffffu, bly, c);
+        const float lz = __shfl_sync(0xffffffffu, blz, c), hx = __shfl_sync(0xffffffffu, bhx, c);
+        const float hy = __shfl_sync(0xffffffffu, bhy, c), hz = __shfl_sync(0xffffffffu, bhz, c);
+        const uint32_t lb = point_box_bits(lx, ly, lz, hx, hy, hz, qx, qy, qz);
+        if (__any_sync(0xffffffffu, active && lb <= my_bound && lb != ICP_INF_BITS)) mask2 |= 1u << c;
     }
-    m = active ? m : 0u;
-    kmin = active ? kmin : 0xffffffffu;
-    m = __reduce_or_sync(0xffffffffu, m);
-    kmin = __reduce_min_sync(0xffffffffu, kmin);
-    pref = (int)(kmin & 7u);   // only used when m != 0, i.e. when some lane passed a child
-    return m;
+    return mask2;
+}
+
+// exact re-test of one child (slot c of record nd) under the current bounds
+__device__ __forceinline__ bool warp_child_recheck(const WideNode* __restrict__ nd, int c, float qx, float qy, float qz,
+                                                   uint32_t my_bound, bool active) {
+    const float* f = reinterpret_cast<const float*>(nd) + c;
+    const uint32_t lb = point_box_bits(__ldg(f), __ldg(f + 8), __ldg(f + 16), __ldg(f + 24), __ldg(f + 32),
+                                       __ldg(f + 40), qx, qy, qz);
+    return __any_sync(0xffffffffu, active && lb <= my_bound && lb != ICP_INF_BITS);
 }
 
 template <typename V>
@@ -122,11 +126,18 @@ __device__ __forceinline__ void wide_traverse_warp(const TreeShape& sh, const Wi
                                                    float qx, float qy, float qz, bool active, V& v) {
     const int top = (int)sh.n_levels - 1;
     if (top == 0) { v.leaf(0); return; }
+    if (!__any_sync(0xffffffffu, active)) return;
+    const float inf = __uint_as_float(ICP_INF_BITS);
+    WarpPatch pb;
+    pb.lox = warp_min_f(active ? qx : inf);  pb.loy = warp_min_f(active ? qy : inf);  pb.loz = warp_min_f(active ? qz : inf);
+    pb.hix = warp_max_f(active ? qx : -inf); pb.hiy = warp_max_f(active ? qy : -inf); pb.hiz = warp_max_f(active ? qz : -inf);
+    uint32_t max_bound = __reduce_max_sync(0xffffffffu, active ? v.bound_bits() : 0u);
+    uint32_t stale = 0;   // bit l: the pending mask of level l predates the latest bound improvement
     int l = top, pref;
     uint32_t i = 0;
     unsigned long long masks =
-        (unsigned long long)warp_child_mask(seg_nodes + sh.level_off[top], qx, qy, qz, v.bound_bits(), active, pref)
-        << (8 * (top - 1));
+        (unsigned long long)warp_node_test(seg_nodes + sh.level_off[top], qx, qy, qz, v.bound_bits(), active, pb,
+                                           max_bound, pref) << (8 * (top - 1));
     for (;;) {
         const int sh8 = 8 * (l - 1);
         const uint32_t m = (uint32_t)(masks >> sh8) & 0xffu;
@@ -139,51 +150,23 @@ __device__ __forceinline__ void wide_traverse_warp(const TreeShape& sh, const Wi
         const int c = (pref >= 0 && ((m >> pref) & 1u)) ? pref : (__ffs((int)m) - 1);
         pref = -1;
         masks &= ~(1ull << (sh8 + c));
+        const WideNode* rec = seg_nodes + sh.level_off[l] + i;
+        if (((stale >> l) & 1u) && !warp_child_recheck(rec, c, qx, qy, qz, v.bound_bits(), active)) continue;
         const uint32_t child = (i << ICP_LOG_FAN) + (uint32_t)c;
         if (l == 1) {
+            const uint32_t before = v.bound_bits();
             v.leaf(child);
+            const uint32_t after = v.bound_bits();
+            if (__any_sync(0xffffffffu, active && after != before)) {
+                stale = 0xffffffffu;
+                max_bound = __reduce_max_sync(0xffffffffu, active ? after : 0u);
+            }
         } else {
             --l; i = child;
-            const uint32_t cm =
-                warp_child_mask(seg_nodes + sh.level_off[l] + i, qx, qy, qz, v.bound_bits(), active, pref);
+            const uint32_t cm = warp_node_test(seg_nodes + sh.level_off[l] + i, qx, qy, qz, v.bound_bits(), active, pb,
+                                               max_bound, pref);
             masks |= (unsigned long long)cm << (8 * (l - 1));
-        }
-    }
-}
-
-// Generic exact walk.  V supplies bound_bits() (current pruning bound, ordered bits) and
-// leaf(g) (offer the 8 points of leaf group g).
-template <typename V>
-__device__ __forceinline__ void wide_traverse(const TreeShape& sh, const WideNode* __restrict__ seg_nodes,
-                                              float qx, float qy, float qz, V& v) {
-    const int top = (int)sh.n_levels - 1;
-    if (top == 0) { v.leaf(0); return; }       // a single leaf group, no internal node
-    int l = top, pref;
-    uint32_t i = 0;
-    unsigned long long masks =
-        (unsigned long long)child_mask(seg_nodes + sh.level_off[top], qx, qy, qz, v.bound_bits(), pref) << (8 * (top - 1));
-    for (;;) {
-        const int sh8 = 8 * (l - 1);
-        const uint32_t m = (uint32_t)(masks >> sh8) & 0xffu;
-        if (m == 0) {
-            if (l == top) break;
-            ++l; i >>= ICP_LOG_FAN;
-            pref = -1;
-            continue;
-        }
-        // first pop after a node was opened: its nearest child if it is pending (the index rides in
-        // the low bound bits, so a near-tie may name a child that just missed the mask); afterwards
-        // lowest index first
-        const int c = (pref >= 0 && ((m >> pref) & 1u)) ? pref : (__ffs((int)m) - 1);
-        pref = -1;
-        masks &= ~(1ull << (sh8 + c));
-        const uint32_t child = (i << ICP_LOG_FAN) + (uint32_t)c;
-        if (l == 1) {
-            v.leaf(child);
-        } else {
-            --l; i = child;
-            const uint32_t cm = child_mask(seg_nodes + sh.level_off[l] + i, qx, qy, qz, v.bound_bits(), pref);
-            masks |= (unsigned long long)cm << (8 * (l - 1));   // that byte is empty: its node was exhausted
+            stale &= ~(1u << l);
         }
     }
 }
@@ -203,14 +186,6 @@ __device__ __forceinline__ void nn_traverse_warp(const TreeShape& sh, const Wide
                                                  bool active, Best& b) {
     NNVisitor v{b, seg_pts, qx, qy, qz};
     wide_traverse_warp(sh, seg_nodes, qx, qy, qz, active, v);
-}
-
-// per-thread variant (independent walks)
-__device__ __forceinline__ void nn_traverse(const TreeShape& sh, const WideNode* __restrict__ seg_nodes,
-                                            const float4* __restrict__ seg_pts, float qx, float qy, float qz,
-                                            Best& b) {
-    NNVisitor v{b, seg_pts, qx, qy, qz};
-    wide_traverse(sh, seg_nodes, qx, qy, qz, v);
 }
 
 // ---- k nearest: ascending list of keys (d2 bits << 32 | original index), k <= KMAX at run time ----
@@ -283,12 +258,4 @@ __device__ __forceinline__ void knn_traverse_warp(const TreeShape& sh, const Wid
                                                   int k, uint32_t g_lo, uint32_t g_hi, bool active, KList<KMAX>& L) {
     KnnVisitor<KMAX> v{L, seg_pts, qx, qy, qz, k, g_lo, g_hi};
     wide_traverse_warp(sh, seg_nodes, qx, qy, qz, active, v);
-}
-
-template <int KMAX>
-__device__ __forceinline__ void knn_traverse(const TreeShape& sh, const WideNode* __restrict__ seg_nodes,
-                                             const float4* __restrict__ seg_pts, float qx, float qy, float qz,
-                                             int k, uint32_t g_lo, uint32_t g_hi, KList<KMAX>& L) {
-    KnnVisitor<KMAX> v{L, seg_pts, qx, qy, qz, k, g_lo, g_hi};
-    wide_traverse(sh, seg_nodes, qx, qy, qz, v);
 }
