@@ -101,13 +101,38 @@ __device__ __forceinline__ uint32_t warp_node_test(const WideNode* __restrict__ 
     pref = (int)(kmin & 7u);
     // stage 2: exact, per lane, only for the survivors
     uint32_t mask2 = 0;
-    for (uint32_t mm = mask1; mm; mm &= mm - 1) {
-        const int c = __ffs((int)mm) - 1;
-        const float lx = __shfl_sync(0xffffffffu, blx, c), ly = __shfl_sync(0xffffffffu, bly, c);
-        const float lz = __shfl_sync(0xffffffffu, blz, c), hx = __shfl_sync(0xffffffffu, bhx, c);
-        const float hy = __shfl_sync(0xffffffffu, bhy, c), hz = __shfl_sync(0xffffffffu, bhz, c);
-        const uint32_t lb = point_box_bits(lx, ly, lz, hx, hy, hz, qx, qy, qz);
-        if (__any_sync(0xffffffffu, active && lb <= my_bound && lb != ICP_INF_BITS)) mask2 |= 1u << c;
+    if (__popc(mask1) > 3) {
+        // dense case (queries far from the surface: the patch box prunes little): all 8 children at
+        // once from 12 uniform 16-byte loads, no shuffles and no loop
+        const float4* p4 = reinterpret_cast<const float4*>(nd);
+        float4 r[12];
+#pragma unroll
+        for (int j = 0; j < 12; j++) r[j] = ldg4(p4 + j);
+        uint32_t mine = 0;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const float lox[4] = {r[h].x, r[h].y, r[h].z, r[h].w};
+            const float loy[4] = {r[2 + h].x, r[2 + h].y, r[2 + h].z, r[2 + h].w};
+            const float loz[4] = {r[4 + h].x, r[4 + h].y, r[4 + h].z, r[4 + h].w};
+            const float hix[4] = {r[6 + h].x, r[6 + h].y, r[6 + h].z, r[6 + h].w};
+            const float hiy[4] = {r[8 + h].x, r[8 + h].y, r[8 + h].z, r[8 + h].w};
+            const float hiz[4] = {r[10 + h].x, r[10 + h].y, r[10 + h].z, r[10 + h].w};
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const uint32_t lb = point_box_bits(lox[c], loy[c], loz[c], hix[c], hiy[c], hiz[c], qx, qy, qz);
+                mine |= (lb <= my_bound && lb != ICP_INF_BITS) ? (1u << (4 * h + c)) : 0u;
+            }
+        }
+        mask2 = __reduce_or_sync(0xffffffffu, active ? mine : 0u) & mask1;
+    } else {
+        for (uint32_t mm = mask1; mm; mm &= mm - 1) {
+            const int c = __ffs((int)mm) - 1;
+            const float lx = __shfl_sync(0xffffffffu, blx, c), ly = __shfl_sync(0xffffffffu, bly, c);
+            const float lz = __shfl_sync(0xffffffffu, blz, c), hx = __shfl_sync(0xffffffffu, bhx, c);
+            const float hy = __shfl_sync(0xffffffffu, bhy, c), hz = __shfl_sync(0xffffffffu, bhz, c);
+            const uint32_t lb = point_box_bits(lx, ly, lz, hx, hy, hz, qx, qy, qz);
+            if (__any_sync(0xffffffffu, active && lb <= my_bound && lb != ICP_INF_BITS)) mask2 |= 1u << c;
+        }
     }
     return mask2;
 }
