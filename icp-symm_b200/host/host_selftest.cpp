@@ -1,0 +1,65 @@
+// host_selftest.cpp -- CPU-only checks of the host logic (PCD I/O); run by tests/test_host.py.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+#include "pcd_io.h"
+
+using namespace icpsymm;
+
+#define CHECK(c) do { if (!(c)) { fprintf(stderr, "FAILED %s:%d: %s\n", __FILE__, __LINE__, #c); return 1; } } while (0)
+
+int main(int argc, char** argv) {
+    const std::string dir = argc > 1 ? argv[1] : "/tmp";
+    PointCloud<PointXYZ> c;
+    PointCloud<Normal> n;
+    for (int i = 0; i < 1000; i++) {
+        PointXYZ p; p.x = std::sin(i * 0.37f) * 123.456f; p.y = 1e-7f * i - 3.0f; p.z = (float)i / 3.0f;
+        Normal m; m.normal_x = std::cos(i * 1.f); m.normal_y = 0.25f; m.normal_z = -m.normal_x; m.curvature = 1e-3f * i;
+        c.points.push_back(p); n.points.push_back(m);
+    }
+    for (int binary = 0; binary < 2; binary++)
+        for (int with_n = 0; with_n < 2; with_n++) {
+            std::string path = dir + "/selftest_" + std::to_string(binary) + std::to_string(with_n) + ".pcd";
+            CHECK(savePCDFile(path, c, with_n ? &n : nullptr, binary != 0) == 0);
+            PointCloud<PointXYZ> r; PointCloud<Normal> rn;
+            CHECK(loadPCDFile(path, r, &rn) == 0);
+            CHECK(r.points.size() == c.points.size());
+            for (size_t i = 0; i < r.points.size(); i++) {      // bit-exact round trip (ascii uses %.9g)
+                CHECK(memcmp(&r.points[i].x, &c.points[i].x, 12) == 0);
+                if (with_n) CHECK(memcmp(&rn.points[i], &n.points[i], 16) == 0);
+            }
+            CHECK(rn.points.size() == (with_n ? c.points.size() : 0));
+        }
+    // the cat_out.pcd layout: 8 fields incl. an unsigned label (cat_out.pcd:3-6); extras are dropped
+    {
+        std::string path = dir + "/selftest_fields.pcd";
+        FILE* f = fopen(path.c_str(), "w");
+        fprintf(f, "# .PCD v0.7 - Point Cloud Data file format\nVERSION 0.7\nFIELDS x y z label normal_x normal_y normal_z curvature\n"
+                   "SIZE 4 4 4 4 4 4 4 4\nTYPE F F F U F F F F\nCOUNT 1 1 1 1 1 1 1 1\nWIDTH 2\nHEIGHT 1\nVIEWPOINT 0 0 0 1 0 0 0\n"
+                   "POINTS 2\nDATA ascii\n-24.415962 3.1901522 30.919439 0 0 0 0 0\n1 2 3 7 0 0 1 0.5\n");
+        fclose(f);
+        PointCloud<PointXYZ> r; PointCloud<Normal> rn;
+        CHECK(loadPCDFile(path, r, &rn) == 0 && r.points.size() == 2);
+        CHECK(r.points[0].x == -24.415962f && r.points[1].z == 3.f && rn.points[1].normal_z == 1.f && rn.points[1].curvature == 0.5f);
+    }
+    PointCloud<PointXYZ> bad;
+    CHECK(loadPCDFile(dir + "/does_not_exist.pcd", bad) != 0);   // the reference ignores this (myicp.cpp:23)
+    {
+        std::string path = dir + "/selftest_trunc.pcd";
+        FILE* f = fopen(path.c_str(), "w");
+        fprintf(f, "VERSION 0.7\nFIELDS x y z\nSIZE 4 4 4\nTYPE F F F\nCOUNT 1 1 1\nWIDTH 3\nHEIGHT 1\nPOINTS 3\nDATA ascii\n1 2 3\n4 5 6\n");
+        fclose(f);
+        CHECK(loadPCDFile(path, bad) != 0);                      // truncated file
+    }
+    {
+        std::string path = dir + "/selftest_za.txt";
+        FILE* f = fopen(path.c_str(), "w");
+        fprintf(f, "-3.03387\t-3.03879\t-2.05533\n-3.03776\t-3.03882\t-2.05536\n");
+        fclose(f);
+        PointCloud<PointXYZ> t;
+        CHECK(loadXYZText(path, t) == 0 && t.points.size() == 2 && t.points[1].y == -3.03882f);
+    }
+    printf("host selftest ok\n");
+    return 0;
+}

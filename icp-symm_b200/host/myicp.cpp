@@ -1,0 +1,156 @@
+#include "myicp.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "../../include/icpsymm.h"
+#include "pcd_io.h"
+
+namespace icpsymm {
+
+// myicp.cpp:6: max_iters(10), diff_threshold(1.f)
+MyICP::MyICP(int device) : max_iters(10), diff_threshold(1.f) {
+    cloud_src = std::make_shared<PointCloud<PointT>>();
+    cloud_tgt = std::make_shared<PointCloud<PointT>>();
+    result_.transform = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    status_ = icpsymm_create(&ctx_, device);
+    if (status_ != ICPSYMM_OK) ctx_ = nullptr;   // no CPU fallback: every later call reports the error
+}
+
+MyICP::~MyICP() {
+    if (ctx_) icpsymm_destroy(ctx_);
+}
+
+const char* MyICP::LastError() const { return ctx_ ? icpsymm_last_error(ctx_) : icpsymm_status_string(status_); }
+
+// myicp.cpp:20-31 (which ignores the reader's return codes and always returns 0)
+int MyICP::LoadCloud(std::string src_path, std::string tgt_path) {
+    int rc = loadPCDFile(src_path, *cloud_src);
+    if (rc != 0) { fprintf(stderr, "Couldn't read file %s\n", src_path.c_str()); return rc; }
+    rc = loadPCDFile(tgt_path, *cloud_tgt);
+    if (rc != 0) { fprintf(stderr, "Couldn't read file %s\n", tgt_path.c_str()); return rc; }
+    uploaded_ = false;
+    return 0;
+}
+
+void MyICP::SetClouds(PointCloud<PointT>::Ptr src, PointCloud<PointT>::Ptr tgt) {
+    cloud_src = src;
+    cloud_tgt = tgt;
+    uploaded_ = false;
+}
+
+PointCloud<PointT>::Ptr MyICP::GetSrcCloud() { return this->cloud_src; }
+PointCloud<PointT>::Ptr MyICP::GetTgtCloud() { return this->cloud_tgt; }
+
+int MyICP::upload() {
+    if (!ctx_) return status_;
+    if (uploaded_) return ICPSYMM_OK;
+    if (cloud_src->empty() || cloud_tgt->empty()) return status_ = ICPSYMM_ERR_NOT_READY;
+    status_ = icpsymm_set_source(ctx_, &cloud_src->points[0].x, cloud_src->size(), sizeof(PointT));
+    if (status_ < 0) return status_;
+    status_ = icpsymm_set_target(ctx_, &cloud_tgt->points[0].x, cloud_tgt->size(), sizeof(PointT));
+    if (status_ < 0) return status_;
+    uploaded_ = true;
+    return status_;
+}
+
+// myicp.cpp:152-172: NormalEstimation, setKSearch(10), viewpoint (0,0,0)
+void MyICP::estimateNormals() {
+    if (upload() < 0) return;
+    status_ = icpsymm_estimate_normals(ctx_, 10, nullptr);
+}
+
+void MyICP::SetRelativeTolerance(double tol) {
+    if (ctx_) icpsymm_set_option(ctx_, ICPSYMM_OPT_REL_DIFF_TOL, tol);
+}
+
+void MyICP::printResult(const char* title) const {
+    if (!verbose_) return;
+    const float* T = result_.transform.data();
+    printf("%s\n", title);
+    for (int r = 0; r < 4; r++) printf("%12.6f %12.6f %12.6f %12.6f\n", T[4 * r], T[4 * r + 1], T[4 * r + 2], T[4 * r + 3]);
+    printf("  rotation:\n");
+    for (int r = 0; r < 3; r++) printf("%12.6f %12.6f %12.6f\n", T[4 * r], T[4 * r + 1], T[4 * r + 2]);
+    printf("  translation:\n%12.6f\n%12.6f\n%12.6f\n", T[3], T[7], T[11]);
+}
+
+void MyICP::RegisterSymm() { RegisterSymm(max_iters, diff_threshold); }
+
+// myicp.cpp:100-150
+void MyICP::RegisterSymm(int iters, float threshold) {
+    estimateNormals();                                   // :105
+    if (status_ < 0) { fprintf(stderr, "RegisterSymm: %s\n", LastError()); return; }
+    icpsymm_stats st;
+    float T[16];
+    status_ = icpsymm_register_symm(ctx_, iters, threshold, T, &st);   // :117-142
+    if (status_ < 0) { fprintf(stderr, "RegisterSymm: %s\n", LastError()); return; }
+    memcpy(result_.transform.data(), T, sizeof T);
+    result_.iterations = st.iters; result_.converged = st.converged; result_.degenerate = st.degenerate != 0;
+    result_.diff = st.diff; result_.rmse = st.rmse; result_.loop_ms = st.loop_ms;
+    if (verbose_) printf("iters# %d\ndiff: %g\n", st.iters, st.diff);     // :125-126
+    printResult("Result transform:");                    // :146-149
+}
+
+void MyICP::RegisterP2P() { RegisterP2P(max_iters, diff_threshold); }
+
+// The reference's RegisterP2P (myicp.cpp:43-59) only applies an identity guess.  This is the
+// point-to-point loop it stands for: exact correspondences on the device, closed-form fit of the
+// matched pairs (registrateNPoint, regist.h:8-72) on the device, repeat.
+void MyICP::RegisterP2P(int iters, float threshold) {
+    if (upload() < 0) { fprintf(stderr, "RegisterP2P: %s\n", LastError()); return; }
+    const size_t n = cloud_src->size();
+    std::vector<int32_t> idx(n);
+    std::vector<float> moved(3 * n);
+    std::vector<double> a(3 * n), b(3 * n);
+    double Tt[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    int it = 0;
+    double diff = 0;
+    for (;;) {
+        float Tf[16];
+        for (int i = 0; i < 16; i++) Tf[i] = (float)Tt[i];
+        status_ = icpsymm_find_correspondences(ctx_, Tf, idx.data(), nullptr);
+        if (status_ < 0) break;
+        status_ = icpsymm_eval_diff(ctx_, Tf, &diff);
+        if (status_ < 0) break;
+        if (verbose_) printf("iters# %d\ndiff: %g\n", it, diff);
+        if (!(diff > threshold) || it >= iters) break;
+        status_ = icpsymm_get_transformed_source(ctx_, Tf, moved.data(), 12);
+        if (status_ < 0) break;
+        size_t m = 0;
+        for (size_t i = 0; i < n; i++) {
+            if (idx[i] < 0) continue;
+            const PointT& q = cloud_tgt->points[(size_t)idx[i]];
+            a[3 * m] = moved[3 * i]; a[3 * m + 1] = moved[3 * i + 1]; a[3 * m + 2] = moved[3 * i + 2];
+            b[3 * m] = q.x; b[3 * m + 1] = q.y; b[3 * m + 2] = q.z;
+            m++;
+        }
+        double R[9], t[3];
+        status_ = icpsymm_register_npoint(ctx_, a.data(), b.data(), m, R, t);
+        if (status_ < 0) break;
+        double inc[16] = {R[0], R[1], R[2], t[0], R[3], R[4], R[5], t[1], R[6], R[7], R[8], t[2], 0, 0, 0, 1}, out[16];
+        for (int r = 0; r < 4; r++)
+            for (int c = 0; c < 4; c++) {
+                double s = 0;
+                for (int k = 0; k < 4; k++) s += inc[4 * r + k] * Tt[4 * k + c];
+                out[4 * r + c] = s;
+            }
+        memcpy(Tt, out, sizeof out);
+        it++;
+    }
+    if (status_ < 0) { fprintf(stderr, "RegisterP2P: %s\n", LastError()); return; }
+    for (int i = 0; i < 16; i++) result_.transform[i] = (float)Tt[i];
+    result_.iterations = it; result_.diff = diff; result_.converged = !(diff > threshold);
+    result_.rmse = 0; result_.degenerate = false;
+    printResult("guess matrix:");                        // myicp.cpp:53
+}
+
+int MyICP::ApplyTransformToSource() {
+    if (upload() < 0) return status_;
+    status_ = icpsymm_get_transformed_source(ctx_, result_.transform.data(), &cloud_src->points[0].x, sizeof(PointT));
+    uploaded_ = false;   // the source cloud changed on the host
+    return status_;
+}
+
+}  // namespace icpsymm
