@@ -86,7 +86,7 @@ void icpsymm_destroy(icpsymm_ctx* ctx) {
     icp_free_cloudset(ctx->src);
     icp_free_cloudset(ctx->tgt);
     cudaFree(ctx->staging); cudaFree(ctx->keys_a); cudaFree(ctx->keys_b); cudaFree(ctx->vals_a); cudaFree(ctx->vals_b);
-    cudaFree(ctx->cub_temp); cudaFree(ctx->d_flags); cudaFree(ctx->d_state); cudaFree(ctx->d_lp);
+    cudaFree(ctx->cub_temp); cudaFree(ctx->d_flags); cudaFree(ctx->d_state); cudaFree(ctx->d_lp); cudaFree(ctx->d_ctrl);
     cudaFree(ctx->corr_pos); cudaFree(ctx->partial); cudaFree(ctx->gsum); cudaFree(ctx->trace_T);
     cudaFree(ctx->trace_diff); cudaFree(ctx->io_buf);
     if (ctx->h_state) cudaFreeHost(ctx->h_state);
@@ -113,7 +113,7 @@ int icpsymm_set_option(icpsymm_ctx* ctx, int key, double value) {
         case ICPSYMM_OPT_REL_DIFF_TOL: if (value < 0) return ICPSYMM_ERR_INVALID; ctx->opt_rel_diff_tol = value; break;
         case ICPSYMM_OPT_IDENTITY_PAIRS: ctx->opt_identity = value != 0; break;
         case ICPSYMM_OPT_MAX_PAIR_DIST: if (value < 0) return ICPSYMM_ERR_INVALID; ctx->opt_max_pair_dist = (float)value; break;
-        case ICPSYMM_OPT_USE_GRAPH: ctx->opt_use_graph = value != 0; break;
+        case ICPSYMM_OPT_USE_GRAPH: ctx->opt_use_graph = (value == 2) ? 2 : (value != 0); break;
         case ICPSYMM_OPT_KERNEL_TIMING: ctx->opt_kernel_timing = value != 0; break;
         case ICPSYMM_OPT_WARM_START: ctx->opt_warm_start = value != 0; break;
         case ICPSYMM_OPT_TRACE: ctx->opt_trace = value != 0; break;

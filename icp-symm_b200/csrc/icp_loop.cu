@@ -41,7 +41,15 @@ struct NNParams {
     int shard_rank, shard_world;
 };
 
+struct LoopCtrl {
+    unsigned int ticket;      // blocks of K2 that have arrived in this iteration
+    unsigned int done_count;  // pairs that are finished (now or earlier) in this iteration
+};
+
 struct SolveParams {
+    cudaGraphConditionalHandle cond;   // while-node condition (use_cond != 0)
+    LoopCtrl* ctrl;
+    int use_cond;
     SegState* state;
     const LoopParams* lp;
     const double* partial;
@@ -351,13 +359,32 @@ __device__ __forceinline__ int solve_compose_dev(const double* __restrict__ S, c
     return degenerate;
 }
 
+// Device-side loop control: the registration loop is a CUDA-graph WHILE node whose body is
+// [K1, K2].  Every K2 block reports whether its pair is finished; the last block to arrive keeps
+// the loop running while any pair is still iterating (myicp.cpp:123 evaluated on the device).
+__device__ __forceinline__ void loop_ctrl_arrive(const SolveParams& P, bool pair_done) {
+    if (!P.use_cond) return;
+    if (pair_done) atomicAdd(&P.ctrl->done_count, 1u);
+    __threadfence();
+    const unsigned int t = atomicAdd(&P.ctrl->ticket, 1u);
+    if (t == gridDim.x - 1) {
+        const unsigned int done = atomicAdd(&P.ctrl->done_count, 0u);
+        P.ctrl->ticket = 0u;
+        P.ctrl->done_count = 0u;
+        cudaGraphSetConditional(P.cond, done < gridDim.x ? 1u : 0u);
+    }
+}
+
 __global__ void __launch_bounds__(kSolveThreads) solve_kernel(const __grid_constant__ SolveParams P) {
     const uint32_t seg = blockIdx.x;
     SegState* st = P.state + seg;
     __shared__ double sPart[kSolveParts][ICP_NSUMS];
     __shared__ double sS[ICP_NSUMS];
     const int tid = threadIdx.x;
-    if (st->done) return;
+    if (st->done) {
+        if (tid == 0) loop_ctrl_arrive(P, true);
+        return;
+    }
     if (P.mode != 2) {
         const int v = tid % ICP_NSUMS, part = tid / ICP_NSUMS;
         if (part < kSolveParts) {
@@ -392,11 +419,16 @@ __global__ void __launch_bounds__(kSolveThreads) solve_kernel(const __grid_const
         for (int i = 0; i < 12; i++) tt[i] = st->Tf[i];
         P.trace_diff[(size_t)seg * P.trace_stride + k] = diff;
     }
-    if (P.mode == 3) { st->done = 1; return; }
-    if (!(diff > (double)lp.diff_threshold)) { st->done = 1; st->converged = 1; return; }      // myicp.cpp:123
-    if (st->iter >= lp.max_iters) { st->done = 1; st->converged = 0; return; }                 // iters++ < max_iters
-    if (lp.rel_diff_tol > 0.0 && k > 0 && fabs(st->prev_diff - diff) <= lp.rel_diff_tol * st->prev_diff) {
-        st->done = 1; st->converged = 2; return;
+    int stop = 0;
+    if (P.mode == 3) stop = 4;
+    else if (!(diff > (double)lp.diff_threshold)) stop = 1;                                    // myicp.cpp:123
+    else if (st->iter >= lp.max_iters) stop = 3;                                               // iters++ < max_iters
+    else if (lp.rel_diff_tol > 0.0 && k > 0 && fabs(st->prev_diff - diff) <= lp.rel_diff_tol * st->prev_diff) stop = 2;
+    if (stop) {
+        st->done = 1;
+        st->converged = (stop == 1) ? 1 : (stop == 2 ? 2 : 0);
+        loop_ctrl_arrive(P, true);
+        return;
     }
     st->prev_diff = diff;
     double Tinc[12], x[6], ratio;
@@ -412,6 +444,7 @@ __global__ void __launch_bounds__(kSolveThreads) solve_kernel(const __grid_const
     for (int i = 0; i < 12; i++) { st->T[i] = Tn[i]; st->Tf[i] = (float)Tn[i]; }
     st->iter = st->iter + 1;
     st->pairs = (unsigned long long)(sS[36] + 0.5);
+    loop_ctrl_arrive(P, false);
 }
 
 __global__ void solve_compose_kernel(const double* in /*37 sums + 3 origin*/, double* out /*12 T + 6 x + ratio + deg*/) {
@@ -584,6 +617,11 @@ int icp_run_loop(icpsymm_ctx* ctx, int max_iters, float thr, const float* T_init
     sp.src_counts = S.counts; sp.trace_T = ctx->opt_trace ? ctx->trace_T : nullptr;
     sp.trace_diff = ctx->opt_trace ? ctx->trace_diff : nullptr;
     sp.blocks_per_seg = bps; sp.trace_stride = ctx->trace_stride; sp.mode = single_search ? 3 : 0;
+    if (!ctx->d_ctrl) {
+        ICP_CUDA_CHECK(cudaMalloc((void**)&ctx->d_ctrl, 2 * sizeof(unsigned int)));
+        ICP_CUDA_CHECK(cudaMemsetAsync(ctx->d_ctrl, 0, 2 * sizeof(unsigned int), st));
+    }
+    sp.ctrl = (LoopCtrl*)ctx->d_ctrl; sp.use_cond = 0; sp.cond = 0;
 
     const bool use_comm = ctx->nccl_comm != nullptr && ctx->shard_world > 1;
     const bool timing = ctx->opt_kernel_timing != 0;
@@ -608,13 +646,35 @@ int icp_run_loop(icpsymm_ctx* ctx, int max_iters, float thr, const float* T_init
         key.p0 = S.pts; key.p1 = T.pts; key.p2 = ctx->partial; key.p3 = ctx->corr_pos; key.p4 = ctx->d_state;
         key.p5 = ctx->opt_trace ? (const void*)ctx->trace_T : (const void*)T.nodes;
         key.shard_rank = ctx->shard_rank; key.shard_world = ctx->shard_world; key.trace = ctx->opt_trace;
+        key.comm_mode = ctx->opt_use_graph;
         // pointers of the remaining arrays change only together with the ones above (same reserve calls)
         if (!ctx->graph_exec || !(ctx->graph_key == key)) {
             if (ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }
             cudaGraph_t g = nullptr;
-            ICP_CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-            for (int k = 0; k < n_search; k++) launch_iteration(ctx, np, sp, nseg, false, nullptr);
-            ICP_CUDA_CHECK(cudaStreamEndCapture(st, &g));
+            if (ctx->opt_use_graph == 2) {
+                // unrolled graph: (max_iters+1) x [K1,K2], finished pairs turn launches into early exits
+                ICP_CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+                for (int k = 0; k < n_search; k++) launch_iteration(ctx, np, sp, nseg, false, nullptr);
+                ICP_CUDA_CHECK(cudaStreamEndCapture(st, &g));
+            } else {
+                // WHILE node: body [K1,K2] repeats until K2 clears the condition on the device
+                ICP_CUDA_CHECK(cudaGraphCreate(&g, 0));
+                cudaGraphConditionalHandle handle;
+                ICP_CUDA_CHECK(cudaGraphConditionalHandleCreate(&handle, g, 1, cudaGraphCondAssignDefault));
+                cudaGraphNodeParams cp = {};
+                cp.type = cudaGraphNodeTypeConditional;
+                cp.conditional.handle = handle;
+                cp.conditional.type = cudaGraphCondTypeWhile;
+                cp.conditional.size = 1;
+                cudaGraphNode_t wnode;
+                ICP_CUDA_CHECK(cudaGraphAddNode(&wnode, g, nullptr, 0, &cp));
+                cudaGraph_t body = cp.conditional.phGraph_out[0];
+                SolveParams spc = sp;
+                spc.use_cond = 1; spc.cond = handle;
+                ICP_CUDA_CHECK(cudaStreamBeginCaptureToGraph(st, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+                launch_iteration(ctx, np, spc, nseg, false, nullptr);
+                ICP_CUDA_CHECK(cudaStreamEndCapture(st, nullptr));
+            }
             ICP_CUDA_CHECK(cudaGraphInstantiate(&ctx->graph_exec, g, 0));
             cudaGraphDestroy(g);
             ctx->graph_key = key;

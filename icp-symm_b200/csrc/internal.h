@@ -67,6 +67,7 @@ struct icpsymm_ctx {
     SegState* d_state = nullptr;  size_t state_cap = 0;
     SegState* h_state = nullptr;  size_t h_state_cap = 0;   // pinned mirror
     LoopParams* d_lp = nullptr;
+    void* d_ctrl = nullptr;       // LoopCtrl: ticket + done counter of the device-side loop
     uint32_t* corr_pos = nullptr; size_t corr_cap = 0;
     double* partial = nullptr;    size_t partial_cap = 0;
     double* gsum = nullptr;       size_t gsum_cap = 0;

@@ -64,7 +64,8 @@ enum {
     ICPSYMM_OPT_REL_DIFF_TOL = 1,   /* 0 = off (reference behaviour); stop when |d(k-1)-d(k)| <= tol*d(k-1) */
     ICPSYMM_OPT_IDENTITY_PAIRS = 2, /* 1 = pair row i with row i (what myicp.cpp:128-131 actually does) */
     ICPSYMM_OPT_MAX_PAIR_DIST = 3,  /* 0 = off; reject pairs farther than this */
-    ICPSYMM_OPT_USE_GRAPH = 4,      /* 1 (default) = run the loop as one CUDA graph */
+    ICPSYMM_OPT_USE_GRAPH = 4,      /* 1 (default) = CUDA graph with a device-side WHILE node; 2 = unrolled graph
+                                       ((max_iters+1) x [search, solve] with early exits); 0 = plain stream launches */
     ICPSYMM_OPT_KERNEL_TIMING = 5,  /* 1 = per-kernel CUDA-event timing (forces stream mode) */
     ICPSYMM_OPT_WARM_START = 6,     /* 1 (default) = seed each search with the previous correspondence */
     ICPSYMM_OPT_TRACE = 7,          /* 1 = keep per-search transform + diff (icpsymm_get_trace) */
@@ -84,7 +85,7 @@ int icpsymm_set_option(icpsymm_ctx* ctx, int key, double value);
 int icpsymm_device_info(int device_ordinal, int* sm_count, int* cc_major, int* cc_minor, size_t* total_mem);
 
 /* ---- clouds (MyICP::LoadCloud, myicp.cpp:20-31; pasteInMatrix, func.cpp:5-15) ----
- * Copies the points to the device, Morton-sorts them and builds the search index.  Any normals
+ * Copies the points to the device, sorts them along a Hilbert curve and builds the search index.  Any normals
  * of that cloud are invalidated. */
 int icpsymm_set_source(icpsymm_ctx* ctx, const float* xyz, size_t n, size_t stride_bytes);
 int icpsymm_set_target(icpsymm_ctx* ctx, const float* xyz, size_t n, size_t stride_bytes);
