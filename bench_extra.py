@@ -1,0 +1,160 @@
+"""Extra bench workloads (manual runs; the driver's headline line is bench.py's default workload).
+
+  --workload batch32k : BASELINE config 5 -- a batch of independent 32K-point scan pairs spread over
+                        the ranks (pair-batch data parallel, no collective); metric registered pairs/s.
+  --workload shard16m : BASELINE config 4 -- one 16M-point pair, query-sharded over the ranks against
+                        replicated clouds, 37-value normal equations all-reduced (NCCL) every iteration;
+                        metric correspondences/s.
+"""
+from __future__ import annotations
+
+import json
+import time
+
+import numpy as np
+
+import workloads as wl
+
+MAX_ITERS, REL_TOL = 50, 1e-5
+
+
+def _reduce(torch, dist, world, work, ms):
+    v = torch.tensor([work, ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        w, t = v[:1].clone(), v[1:].clone()
+        dist.all_reduce(w, op=dist.ReduceOp.SUM)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(w), float(t)
+    return float(v[0]), float(v[1])
+
+
+def run_batch(args, rank, world, local_rank, barrier):
+    import torch
+    import torch.distributed as dist
+    import icpsymm as icp
+
+    n = 32768
+    lo, hi = wl.shard_range(args.pairs, rank, world)
+    local = hi - lo
+    distinct = min(local, 64)
+    S = np.empty((local, n, 3), np.float32)
+    T = np.empty((local, n, 3), np.float32)
+    truth = []
+    for j in range(distinct):
+        s, t, Tt = wl.config_batch_pair(lo + j, n)
+        S[j], T[j] = s, t
+        truth.append(Tt)
+    for j in range(distinct, local):          # the remaining pairs repeat the distinct ones (own memory, same work)
+        S[j], T[j] = S[j % distinct], T[j % distinct]
+    hS, hT = torch.from_numpy(S).pin_memory(), torch.from_numpy(T).pin_memory()
+    ctx = icp.Context(local_rank)
+    ctx.set_option(icp.OPT_REL_DIFF_TOL, REL_TOL)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=local_rank)
+    L = ctx.L
+
+    def upload():
+        ctx._check(L.icpsymm_set_source_batch(ctx.h, hS.data_ptr(), None, local, n, 12))
+        ctx._check(L.icpsymm_set_target_batch(ctx.h, hT.data_ptr(), None, local, n, 12))
+        ctx.n_pairs, ctx.n_src, ctx.n_tgt = local, n, n
+        ctx.estimate_normals(10)
+
+    upload()
+    thr = 1e-3
+    for _ in range(max(args.warmup, 1)):
+        Tm, st, _ = ctx.register_symm(MAX_ITERS, thr)
+    barrier()
+    loop_ms = []
+    for _ in range(args.steps):
+        Tm, st, _ = ctx.register_symm(MAX_ITERS, thr)
+        loop_ms.append(st[0]["loop_ms"])
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2e_ms = []
+    for _ in range(max(1, args.steps // 2)):
+        ev0.record(stream)
+        upload()
+        Tm, st, _ = ctx.register_symm(MAX_ITERS, thr)
+        ev1.record(stream)
+        ev1.synchronize()
+        e2e_ms.append(ev0.elapsed_time(ev1))
+    barrier()
+    errs = [wl.rotation_angle(Tm[j], truth[j]) for j in range(distinct)]
+    iters = [s["iters"] for s in st]
+    work, ms = _reduce(torch, dist, world, float(local * len(loop_ms)), float(np.sum(loop_ms)))
+    work2, ms2 = _reduce(torch, dist, world, float(local * len(e2e_ms)), float(np.sum(e2e_ms)))
+    if rank == 0:
+        print(json.dumps({
+            "metric": "registered pairs/sec", "value": work / (ms * 1e-3), "unit": "pairs/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / len(loop_ms), "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"batch of {args.pairs} independent {n}-point pairs (config 5), {local} on rank 0, "
+                                   f"{distinct} distinct per rank", "max_iters": MAX_ITERS, "diff_threshold": thr,
+                       "rel_diff_tol": REL_TOL, "iters_mean": float(np.mean(iters)), "iters_max": int(np.max(iters)),
+                       "max_rot_err_rad": float(np.max(errs))},
+            "e2e": {"value": work2 / (ms2 * 1e-3), "unit": "pairs/s", "ms_per_step": ms2 / len(e2e_ms),
+                    "h2d_bytes_per_step": int(2 * local * n * 12), "d2h_bytes_per_step": int(local * (64 + 72))},
+        }), flush=True)
+    ctx.close()
+
+
+def run_shard(args, rank, world, local_rank, barrier):
+    import torch
+    import torch.distributed as dist
+    import icpsymm as icp
+
+    n = args.points if args.points != 1_000_000 else 16 * 2 ** 20
+    src, tgt, Ttrue = wl.config_synth(n)               # identical on every rank (same seed)
+    ctx = icp.Context(local_rank)
+    ctx.set_option(icp.OPT_REL_DIFF_TOL, REL_TOL)
+    if world > 1:
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid = torch.frombuffer(bytearray(icp.comm_unique_id()), dtype=torch.uint8).cuda()
+        dist.broadcast(uid, 0)
+        ctx.comm_init(bytes(uid.cpu().numpy().tobytes()), world, rank)
+    t0 = time.perf_counter()
+    ctx.set_source(src)
+    ctx.set_target(tgt)
+    ctx.estimate_normals(10)
+    setup_s = time.perf_counter() - t0
+    for _ in range(max(args.warmup, 1)):
+        Tm, st, _ = ctx.register_symm(MAX_ITERS, 1.0)
+    barrier()
+    loop_ms = []
+    for _ in range(args.steps):
+        Tm, st, _ = ctx.register_symm(MAX_ITERS, 1.0)
+        loop_ms.append(st["loop_ms"])
+    barrier()
+    # every rank must hold the same transform
+    tt = torch.from_numpy(np.ascontiguousarray(Tm, np.float32)).cuda()
+    same = True
+    if world > 1:
+        ref = tt.clone()
+        dist.broadcast(ref, 0)
+        flag = torch.tensor([float(torch.equal(ref, tt))], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        same = bool(flag.item() == 1.0)
+    _, ms = _reduce(torch, dist, world, 0.0, float(np.sum(loop_ms)))
+    if rank == 0:
+        print(json.dumps({
+            "metric": "correspondences/sec (NN+symm solve)", "value": float(n) * st["iters"] * len(loop_ms) / (ms * 1e-3),
+            "unit": "correspondences/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / len(loop_ms), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"synth-{n} pair query-sharded over {world} ranks, replicated clouds, "
+                                   "NCCL all-reduce of 37 fp64 sums per iteration (config 4)",
+                       "iters_run": st["iters"], "setup_s_per_rank": setup_s, "identical_transform_on_all_ranks": same,
+                       "rot_err_rad": wl.rotation_angle(Tm, Ttrue)},
+        }), flush=True)
+    ctx.close()
+
+
+def run(args, rank, world, local_rank, barrier):
+    import torch.distributed as dist
+    if args.workload == "batch32k":
+        run_batch(args, rank, world, local_rank, barrier)
+    else:
+        run_shard(args, rank, world, local_rank, barrier)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
