@@ -38,7 +38,7 @@ __device__ __forceinline__ void jacobi_rotate(float& app, float& aqq, float& apq
     }
 }
 
-template <int KMAX>
+template <int KMAX, bool EXACT>
 __global__ void __launch_bounds__(128) normals_kernel(const __grid_constant__ NormalParams P) {
     // one block = 128 consecutive sorted points of ONE segment, so that a warp never straddles two
     // clouds and its 32 lanes can walk the hierarchy together
@@ -55,23 +55,27 @@ __global__ void __launch_bounds__(128) normals_kernel(const __grid_constant__ No
     const int k = P.k;
 
     // first bound: the query's own leaf group and its neighbours along the curve
-    KList<KMAX> L;
+    KList<KMAX, EXACT> L;
     L.init();
     const uint32_t n_groups = pitch / ICP_LEAF;
     const uint32_t g = active ? i / ICP_LEAF : 0u, w = (k <= 16) ? 1u : 2u;
     const uint32_t g_lo = g >= w ? g - w : 0u, g_hi = (g + w < n_groups) ? g + w : n_groups - 1;
-    if (active) {
-        for (uint32_t gg = g_lo; gg <= g_hi; gg++) {
-            const float4* lp = pts + (size_t)gg * ICP_LEAF;
-#pragma unroll
-            for (int t = 0; t < ICP_LEAF; t++) {
-                float4 c = ldg4(lp + t);
-                uint32_t id = __float_as_uint(c.w);
-                if (id != (uint32_t)ICP_INVALID_ID) L.offer(k, dist2_rn(q.x, q.y, q.z, c.x, c.y, c.z), id);
+    // lanes of one warp cover at most 5 consecutive leaf groups; walk the union of their windows
+    {
+        const uint32_t w_lo = __reduce_min_sync(0xffffffffu, active ? g_lo : 0xffffffffu);
+        const uint32_t w_hi = __reduce_max_sync(0xffffffffu, active ? g_hi : 0u);
+        if (w_lo != 0xffffffffu) {
+#pragma unroll 1
+            for (uint32_t gg = w_lo; gg <= w_hi; gg++) {
+                const bool mine = active && gg >= g_lo && gg <= g_hi;
+                const unsigned long long saved = L.kth;
+                if (!mine) L.kth = 0ull;
+                knn_offer_leaf(L, k, pts + (size_t)gg * ICP_LEAF, q.x, q.y, q.z);
+                if (!mine) L.kth = saved;
             }
         }
     }
-    knn_traverse_warp<KMAX>(P.cloud.shape, boxes, pts, q.x, q.y, q.z, k, g_lo, g_hi, active, L);
+    knn_traverse_warp<KMAX, EXACT>(P.cloud.shape, boxes, pts, q.x, q.y, q.z, k, g_lo, g_hi, active, L);
     if (!active) return;
 
     // covariance of the neighbourhood, coordinates relative to the query point
@@ -166,9 +170,10 @@ int icp_estimate_normals(icpsymm_ctx* ctx, CloudSet& cs, int k, const float vp[3
     size_t slots = (size_t)cs.nseg * cs.shape.pitch;
     uint32_t grid = cs.nseg * ((cs.shape.pitch + 127u) / 128u);
     ICP_CUDA_CHECK(cudaMemsetAsync(cs.nrm, 0, slots * sizeof(float4), ctx->stream));
-    if (k <= 10) normals_kernel<10><<<grid, 128, 0, ctx->stream>>>(P);
-    else if (k <= 16) normals_kernel<16><<<grid, 128, 0, ctx->stream>>>(P);
-    else normals_kernel<32><<<grid, 128, 0, ctx->stream>>>(P);
+    if (k == 10) normals_kernel<10, true><<<grid, 128, 0, ctx->stream>>>(P);       // the reference's k (myicp.cpp:160)
+    else if (k < 10) normals_kernel<10, false><<<grid, 128, 0, ctx->stream>>>(P);
+    else if (k <= 16) normals_kernel<16, false><<<grid, 128, 0, ctx->stream>>>(P);
+    else normals_kernel<32, false><<<grid, 128, 0, ctx->stream>>>(P);
     ICP_CUDA_CHECK(cudaGetLastError());
     cs.has_normals = true;
     return ICPSYMM_OK;

@@ -215,7 +215,9 @@ __device__ __forceinline__ void nn_traverse_warp(const TreeShape& sh, const Wide
 
 // ---- k nearest: ascending list of keys (d2 bits << 32 | original index), k <= KMAX at run time ----
 // d2 >= 0 or +inf, so its bit pattern orders like an unsigned integer; an unfilled slot is ~0.
-template <int KMAX>
+// EXACT = the list is used with k == KMAX (the reference's k = 10, myicp.cpp:160): no per-slot
+// `j < k` predicate and the k-th best is simply the last slot.
+template <int KMAX, bool EXACT>
 struct KList {
     unsigned long long key[KMAX];
     unsigned long long kth;  // key[k-1]: the current k-th best
@@ -225,62 +227,100 @@ struct KList {
         for (int j = 0; j < KMAX; j++) key[j] = ~0ull;
         kth = ~0ull;
     }
-    __device__ __forceinline__ void offer(int k, float d2, uint32_t id) {
-        unsigned long long kk = ((unsigned long long)__float_as_uint(d2) << 32) | id;
-        if (kk >= kth) return;
-        // carry-insert: every slot keeps the smaller of (carry, slot) and passes the larger on
-        unsigned long long cur = kk;
+    // sorted insert of a key that is known to be < kth: slot j keeps its key while it is smaller
+    // than the new one, otherwise it takes the new key (first such slot) or its left neighbour
+    __device__ __forceinline__ void insert(int k, unsigned long long kk) {
+        bool prev_less = true;   // "key[j-1] < kk" for j = 0
+        unsigned long long prev_key = 0ull;
 #pragma unroll
         for (int j = 0; j < KMAX; j++) {
-            if (j < k) {
-                unsigned long long a = key[j];
-                bool sw = cur < a;
-                key[j] = sw ? cur : a;
-                cur = sw ? a : cur;
+            const unsigned long long cur = key[j];
+            const bool less = cur < kk;
+            if (EXACT || j < k) key[j] = less ? cur : (prev_less ? kk : prev_key);
+            prev_less = less;
+            prev_key = cur;
+        }
+        if (EXACT) {
+            kth = key[KMAX - 1];
+        } else {
+            // k-th best = max of the first k slots (written as a max so the compiler keeps key[] in
+            // registers instead of turning a select chain into a dynamic local-memory index)
+            unsigned long long t = 0ull;
+#pragma unroll
+            for (int j = 0; j < KMAX; j++) {
+                unsigned long long c = (j < k) ? key[j] : 0ull;
+                t = c > t ? c : t;
             }
+            kth = t;
         }
-        // k-th best = max of the first k slots (written as a max so the compiler keeps key[] in
-        // registers instead of turning a select chain into a dynamic local-memory index)
-        unsigned long long t = 0ull;
-#pragma unroll
-        for (int j = 0; j < KMAX; j++) {
-            unsigned long long c = (j < k) ? key[j] : 0ull;
-            t = c > t ? c : t;
-        }
-        kth = t;
+    }
+    __device__ __forceinline__ void offer(int k, float d2, uint32_t id) {
+        const unsigned long long kk = ((unsigned long long)__float_as_uint(d2) << 32) | id;
+        if (kk < kth) insert(k, kk);
     }
     __device__ __forceinline__ uint32_t bound_bits() const { return (uint32_t)(kth >> 32); }
 };
 
-// Leaves [g_lo, g_hi] were already offered by the caller (the query's own neighbourhood along the curve,
-// which gives a finite first bound) and are skipped so that no candidate enters the list twice.
-// Sentinel padding points are ignored.
-template <int KMAX>
+// offer the 8 points of one leaf group.  The 8 keys are formed first; then, round by round, every
+// lane inserts its smallest still-unseen key that beats its k-th best.  The number of rounds is the
+// largest number of insertions any lane needs (usually 0-2), so the long insertion body is executed
+// that many times per leaf instead of up to 8 times, and it exists once in the instruction stream.
+template <int KMAX, bool EXACT>
+__device__ __forceinline__ void knn_offer_leaf(KList<KMAX, EXACT>& L, int k, const float4* __restrict__ lp,
+                                               float qx, float qy, float qz) {
+    unsigned long long kk[ICP_LEAF];
+#pragma unroll
+    for (int j = 0; j < ICP_LEAF; j++) {
+        const float4 c = ldg4(lp + j);
+        const uint32_t id = __float_as_uint(c.w);
+        const float d = dist2_rn(qx, qy, qz, c.x, c.y, c.z);
+        kk[j] = (id != (uint32_t)ICP_INVALID_ID) ? (((unsigned long long)__float_as_uint(d) << 32) | id) : ~0ull;
+    }
+    unsigned long long floor_key = 0ull;   // keys <= floor_key were handled in earlier rounds
+    bool first = true;
+#pragma unroll 1
+    for (;;) {
+        unsigned long long best = ~0ull;
+#pragma unroll
+        for (int j = 0; j < ICP_LEAF; j++) {
+            const bool fresh = first || kk[j] > floor_key;
+            best = (fresh && kk[j] < best) ? kk[j] : best;
+        }
+        const bool go = best < L.kth;
+        if (!__any_sync(0xffffffffu, go)) break;
+        if (go) L.insert(k, best);
+        floor_key = best;
+        first = false;
+    }
+}
+
+// Leaves [g_lo, g_hi] were already offered by the caller (the query's own neighbourhood along the
+// curve, which gives a finite first bound) and are skipped so that no candidate enters the list
+// twice.  Sentinel padding points are ignored.
+template <int KMAX, bool EXACT>
 struct KnnVisitor {
-    KList<KMAX>& L;
+    KList<KMAX, EXACT>& L;
     const float4* __restrict__ pts;
     float qx, qy, qz;
     int k;
     uint32_t g_lo, g_hi;
+    bool active;
     __device__ __forceinline__ uint32_t bound_bits() const { return L.bound_bits(); }
     __device__ __forceinline__ void leaf(uint32_t g) {
-        if (g >= g_lo && g <= g_hi) return;
-        const float4* lp = pts + (size_t)g * ICP_LEAF;
-        float4 c[ICP_LEAF];
-#pragma unroll
-        for (int j = 0; j < ICP_LEAF; j++) c[j] = ldg4(lp + j);
-#pragma unroll
-        for (int j = 0; j < ICP_LEAF; j++) {
-            uint32_t id = __float_as_uint(c[j].w);
-            if (id != (uint32_t)ICP_INVALID_ID) L.offer(k, dist2_rn(qx, qy, qz, c[j].x, c[j].y, c[j].z), id);
-        }
+        // warp-uniform call; a lane skips the leaves it has already seen by making its keys inert
+        const bool skip = !active || (g >= g_lo && g <= g_hi);
+        const unsigned long long saved = L.kth;
+        if (skip) L.kth = 0ull;                 // nothing beats 0: no insertion for this lane
+        knn_offer_leaf(L, k, pts + (size_t)g * ICP_LEAF, qx, qy, qz);
+        if (skip) L.kth = saved;
     }
 };
 
-template <int KMAX>
+template <int KMAX, bool EXACT>
 __device__ __forceinline__ void knn_traverse_warp(const TreeShape& sh, const WideNode* __restrict__ seg_nodes,
                                                   const float4* __restrict__ seg_pts, float qx, float qy, float qz,
-                                                  int k, uint32_t g_lo, uint32_t g_hi, bool active, KList<KMAX>& L) {
-    KnnVisitor<KMAX> v{L, seg_pts, qx, qy, qz, k, g_lo, g_hi};
+                                                  int k, uint32_t g_lo, uint32_t g_hi, bool active,
+                                                  KList<KMAX, EXACT>& L) {
+    KnnVisitor<KMAX, EXACT> v{L, seg_pts, qx, qy, qz, k, g_lo, g_hi, active};
     wide_traverse_warp(sh, seg_nodes, qx, qy, qz, active, v);
 }
