@@ -50,6 +50,16 @@ def measured_peak_gbs():
         return 6650.0, "fallback"
 
 
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
+    `ncu --set full` capture (profiles/r01_nn_accum.json); None when no capture is committed"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_nn_accum.json")) as f:
+            return json.load(f)["dram_bytes_per_launch_mean"]
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """samples nvidia-smi SM clocks + throttle reasons while the timed region runs"""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -96,15 +106,16 @@ def run_reference(args, rank, world):
     from oracle import oracle as orc
     n = args.points
     src, tgt, _ = make_pair(n, 0)
-    sample = min(n, args.cpu_sample or 250_000)
-    sel = np.sort(np.random.default_rng(7).choice(n, sample, replace=False))
+    sample = min(n, args.cpu_sample or n)
+    sel = np.sort(np.random.default_rng(7).choice(n, sample, replace=False)) if sample < n else np.arange(n)
     threads = orc.num_threads()
-    # normals are setup for the loop metric: estimate them once, outside the timed steps
-    ns, _ = orc.estimate_normals(src[sel], 10)
-    nt, _ = orc.estimate_normals(tgt, 10)
     times, iters = [], 0
     for s in range(args.warmup + args.steps):
         t0 = time.perf_counter()
+        # the whole MyICP::RegisterSymm of the reference (myicp.cpp:100-150): normals of both clouds
+        # (kd-tree + kNN-10 + PCA), kd-tree of the target, then the loop -- what our e2e arm times
+        ns, _ = orc.estimate_normals(src[sel], 10, threads=threads)
+        nt, _ = orc.estimate_normals(tgt, 10, threads=threads)
         r = orc.register_symm(src[sel], ns, tgt, nt, max_iters=MAX_ITERS, diff_threshold=DIFF_THR * sample / n,
                               rel_diff_tol=REL_TOL, threads=threads)
         dt = time.perf_counter() - t0
@@ -119,8 +130,8 @@ def run_reference(args, rank, world):
             "config": {"workload": f"synth-{n} bumpy ellipsoid, 30deg/0.1-extent, noise 1e-4 (config 3)",
                        "max_iters": MAX_ITERS, "diff_threshold": DIFF_THR, "rel_diff_tol": REL_TOL, "iters_run": iters},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                             "sample": f"{sample} of {n} source points (random subset) against the full {n}-point target; "
-                                       "whole registration loop per step, kd-tree build included, normals excluded"},
+                             "sample": f"{sample} of {n} source points against the full {n}-point target; every step is the "
+                                       "whole RegisterSymm: k=10 normals of both clouds, kd-tree build, loop"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "PCL-equivalent restatement (exact kd-tree, leaf 15, OpenMP); PCL itself is not installable here"}
     print(json.dumps(line), flush=True)
@@ -203,12 +214,13 @@ def main():
     sampler = ClockSampler(local_rank)
     barrier()
     sampler.start()
-    loop_ms, iters = [], []
+    loop_ms, iters, launches = [], [], 0
     for _ in range(args.steps):
         l2_flush()
         T, st, _ = step_resident()           # stats.loop_ms = CUDA events on the launching stream
         loop_ms.append(st["loop_ms"])
         iters.append(st["iters"])
+        launches += 2 + 2 * st["searches"]   # set_lp + init_state, then [search, solve] per WHILE-body trip
     barrier()
     clocks = sampler.stop()
     my_ms = float(np.sum(loop_ms))
@@ -266,16 +278,17 @@ def main():
             "config": {"workload": f"synth-{n} bumpy ellipsoid, 30deg/0.1-extent, noise 1e-4 (config 3), one pair per GPU",
                        "points": n, "max_iters": MAX_ITERS, "diff_threshold": DIFF_THR, "rel_diff_tol": REL_TOL,
                        "iters_run": int(iters[-1]), "searches_run": int(st["searches"]),
-                       "l2": "flushed between steps (256 MB memset)", "mode": "cuda-graph, device-side done flag",
+                       "l2": "flushed between steps (256 MB memset)",
+                       "mode": "one CUDA graph per step: WHILE node with body [search+accumulate, reduce+solve], condition set on device",
                        "rot_err_rad": rot_err, "trans_err_over_extent": trans_err},
             "clocks": clocks,
             "e2e": {"value": tot_e2e_corr / (max_e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": max_e2e_ms / args.steps,
                     "h2d_bytes_per_step": int(2 * n * 12), "d2h_bytes_per_step": 64 + 2 * 128,
                     "includes": "H2D of both clouds, Morton sort + box hierarchy, kNN-10 normals, loop, D2H transform"},
-            "gpu_launches": int(args.steps * (2 + 2 * (MAX_ITERS + 1))),
+            "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "nn_accum_kernel (fused NN search + symmetric accumulate)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
-                         "peak_kind": f"of {peak_kind}", "traffic": None,
+                         "peak_kind": f"of {peak_kind}", "traffic": ncu_traffic(),
                          "bytes_per_unit": BYTES_PER_CORR_FUSED, "units_per_launch": n,
                          "avg_launch_ms": k_ms / k_launch if k_launch else None, "launches_timed": k_launch,
                          "solve_kernel_avg_ms": s_ms / k_launch if k_launch else None,

@@ -516,7 +516,7 @@ static uint32_t choose_blocks_per_seg(const icpsymm_ctx* ctx, uint32_t nseg, uin
     uint32_t bps;
     if (ctx->opt_grid_blocks > 0) bps = (uint32_t)ctx->opt_grid_blocks;
     else {
-        uint32_t target = (uint32_t)ctx->sm_count * 8u;
+        uint32_t target = (uint32_t)ctx->sm_count * 16u;   // 4 resident blocks/SM x 4 waves: measured best at 1M
         bps = (target + nseg - 1) / nseg;
     }
     if (bps > ntiles) bps = ntiles;

@@ -13,6 +13,7 @@ with icp.Context(0) as ctx:
     ctx.set_option(icp.OPT_REL_DIFF_TOL, 1e-5)
     ctx.set_option(icp.OPT_USE_GRAPH, 0)
     ctx.set_option(icp.OPT_KERNEL_TIMING, 1)
+    if os.environ.get('GRID_BLOCKS'): ctx.set_option(icp.OPT_GRID_BLOCKS, int(os.environ['GRID_BLOCKS']))
     ctx.set_source(src); ctx.set_target(tgt); ctx.estimate_normals(10)
     for _ in range(reps):
         Tm, st, rc = ctx.register_symm(50, 1.0)
