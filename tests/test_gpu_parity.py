@@ -390,3 +390,60 @@ def test_errors_are_reported_not_hidden(ctx, cat):
     with pytest.raises(icp.IcpError):
         c.set_source(np.zeros((0, 3), np.float32))
     c.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE.json full sizes: bit-exact index parity against the oracle kd-tree plus the
+# size-independent properties of the domain
+# ---------------------------------------------------------------------------------------------
+def test_full_size_1m_config3(ctx):
+    src, tgt, Ttrue = wl.config_synth(1_000_000)
+    ctx.set_source(src); ctx.set_target(tgt)
+    tree = orc.KdTree(tgt)
+    # far first search (30 deg / 0.1 extent): every one of the 1M indices and fp32 distances identical
+    idx, d2 = ctx.find_correspondences()
+    oi, od = tree.nn(src)
+    assert np.array_equal(idx, oi) and np.array_equal(d2, od)
+    ctx.estimate_normals(10)
+    ctx.set_option(icp.OPT_REL_DIFF_TOL, 1e-5)
+    try:
+        T, st, _ = ctx.register_symm(50, 1.0)
+        assert 0 < st["iters"] <= 50 and st["converged"] == 2 and st["degenerate"] == 0
+        assert wl.rotation_angle(T, Ttrue) < 2e-5 and np.abs(T[:3, 3] - Ttrue[:3, 3]).max() < 2e-5 * wl.extent(tgt)
+        # final correspondences: bit-exact against the oracle fed with the device transform
+        idx, d2 = ctx.get_correspondences()
+        oi, od = tree.nn(orc.transform_points(T, src))
+        assert np.array_equal(idx, oi) and np.array_equal(d2, od)
+        assert st["rmse"] == pytest.approx(np.sqrt(od.astype(np.float64).mean()), rel=1e-6)
+        assert st["diff"] == pytest.approx(np.sqrt(od.astype(np.float64)).sum(), rel=1e-6)
+        # determinism: a second run is bit-identical
+        T2, st2, _ = ctx.register_symm(50, 1.0)
+        assert np.array_equal(T, T2) and st2["diff"] == st["diff"]
+        # idempotence: registering the aligned source changes (almost) nothing
+        ctx.set_source(orc.transform_points(T, src)); ctx.estimate_normals(10)
+        T3, st3, _ = ctx.register_symm(50, 1.0)
+        assert wl.rotation_angle(T3, np.eye(4)) < 1e-5 and np.abs(T3[:3, 3]).max() < 1e-5 * wl.extent(tgt)
+    finally:
+        ctx.set_option(icp.OPT_REL_DIFF_TOL, 0.0)
+
+
+def test_batch_of_32k_pairs_config5(ctx):
+    B, n = 48, 32768
+    pairs = [wl.config_batch_pair(b, n) for b in range(B)]
+    S = np.stack([p[0] for p in pairs]); Tg = np.stack([p[1] for p in pairs])
+    ctx.set_source_batch(S); ctx.set_target_batch(Tg)
+    ctx.estimate_normals(10)
+    ctx.set_option(icp.OPT_REL_DIFF_TOL, 1e-5)
+    try:
+        T, st, _ = ctx.register_symm(50, 1e-3)
+    finally:
+        ctx.set_option(icp.OPT_REL_DIFF_TOL, 0.0)
+    idx, d2 = ctx.get_correspondences()
+    idx = idx.reshape(B, n)
+    for b in range(B):
+        assert wl.rotation_angle(T[b], pairs[b][2]) < 1e-4, b
+        assert np.abs(T[b][:3, 3] - pairs[b][2][:3, 3]).max() < 1e-4 * wl.extent(Tg[b])
+        assert st[b]["iters"] <= 50 and st[b]["degenerate"] == 0
+    for b in (0, B // 2, B - 1):      # index parity of the final search, per pair
+        oi, _ = orc.KdTree(Tg[b]).nn(orc.transform_points(T[b], S[b]))
+        assert np.array_equal(idx[b], oi)
