@@ -148,6 +148,7 @@ def main():
     ap.add_argument("--pairs", type=int, default=4096)
     ap.add_argument("--cpu-sample", type=int, default=0, help="source points per CPU step (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--comm", default="peer", choices=["peer", "nccl"], help="shard16m: exchange of the normal equations")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 

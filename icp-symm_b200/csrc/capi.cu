@@ -82,6 +82,7 @@ void icpsymm_destroy(icpsymm_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     icpsymm_comm_destroy(ctx);
+    icpsymm_peer_detach(ctx);
     if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
     icp_free_cloudset(ctx->src);
     icp_free_cloudset(ctx->tgt);

@@ -101,3 +101,53 @@ extern "C" int icpsymm_set_query_shard(icpsymm_ctx* ctx, int rank, int n_ranks) 
     ctx->shard_world = n_ranks;
     return ICPSYMM_OK;
 }
+
+// ---- NVLink peer exchange (used by solve_kernel, icp_loop.cu) ------------------------------------
+static size_t peer_buffer_bytes() { return sizeof(PeerSlot) * 2 * ICP_MAX_PEERS; }
+
+extern "C" int icpsymm_peer_export(icpsymm_ctx* ctx, void* handle64_out) {
+    if (!ctx || !handle64_out) return ICPSYMM_ERR_INVALID;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return icp_fail_msg(ctx, ICPSYMM_ERR_CUDA, "cudaSetDevice");
+    if (!ctx->peer_local) {
+        ICP_CUDA_CHECK(cudaMalloc(&ctx->peer_local, peer_buffer_bytes()));
+        ICP_CUDA_CHECK(cudaMemset(ctx->peer_local, 0, peer_buffer_bytes()));
+    }
+    cudaIpcMemHandle_t h;
+    ICP_CUDA_CHECK(cudaIpcGetMemHandle(&h, ctx->peer_local));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    memcpy(handle64_out, &h, 64);
+    return ICPSYMM_OK;
+}
+
+extern "C" int icpsymm_peer_attach(icpsymm_ctx* ctx, const void* handles, int n_ranks, int rank) {
+    if (!ctx || !handles || n_ranks < 1 || n_ranks > ICP_MAX_PEERS || rank < 0 || rank >= n_ranks) return ICPSYMM_ERR_INVALID;
+    if (!ctx->peer_local) return icp_fail_msg(ctx, ICPSYMM_ERR_NOT_READY, "call icpsymm_peer_export first");
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return icp_fail_msg(ctx, ICPSYMM_ERR_CUDA, "cudaSetDevice");
+    for (int r = 0; r < n_ranks; r++) {
+        if (r == rank) { ctx->peer_ptrs[r] = ctx->peer_local; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char*)handles + 64 * (size_t)r, 64);
+        void* p = nullptr;
+        ICP_CUDA_CHECK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        ctx->peer_ptrs[r] = p;
+    }
+    ctx->peer_world = n_ranks;
+    ctx->shard_rank = rank;
+    ctx->shard_world = n_ranks;
+    return ICPSYMM_OK;
+}
+
+extern "C" int icpsymm_peer_detach(icpsymm_ctx* ctx) {
+    if (!ctx) return ICPSYMM_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (int r = 0; r < ICP_MAX_PEERS; r++) {
+        if (ctx->peer_ptrs[r] && ctx->peer_ptrs[r] != ctx->peer_local) cudaIpcCloseMemHandle(ctx->peer_ptrs[r]);
+        ctx->peer_ptrs[r] = nullptr;
+    }
+    if (ctx->peer_local) { cudaFree(ctx->peer_local); ctx->peer_local = nullptr; }
+    if (ctx->peer_world > 1) { ctx->shard_rank = 0; ctx->shard_world = 1; }
+    ctx->peer_world = 0;
+    cudaGetLastError();
+    return ICPSYMM_OK;
+}

@@ -22,6 +22,15 @@
 #define ICP_NSUMS 37
 #define ICP_PART_STRIDE 40               // doubles per partial-sum row (37 padded)
 #define ICP_INVALID_ID 0x7fffffff
+#define ICP_MAX_PEERS 8                  // one NVSwitch domain
+
+// exchange slot of the NVLink peer mode: rank r writes its sums of iteration `seq` into slot
+// [seq & 1][r] of every rank's buffer, then publishes seq
+struct __align__(128) PeerSlot {
+    double sums[ICP_PART_STRIDE];
+    unsigned long long seq;
+    unsigned long long pad[7];
+};
 
 // boxes of the 8 children of one internal node, structure-of-arrays so that one node is 12
 // independent 16-byte loads and the 8 bounds are computed together

@@ -44,6 +44,9 @@ struct NNParams {
 struct LoopCtrl {
     unsigned int ticket;      // blocks of K2 that have arrived in this iteration
     unsigned int done_count;  // pairs that are finished (now or earlier) in this iteration
+    unsigned long long seq;   // number of peer exchanges done so far (identical on every rank)
+    int comm_error;           // a peer did not answer in time
+    int pad;
 };
 
 struct SolveParams {
@@ -60,6 +63,8 @@ struct SolveParams {
     uint32_t blocks_per_seg;
     int trace_stride;
     int mode;  // 0 reduce+solve, 1 reduce only (-> gsum), 2 solve from gsum, 3 reduce + record, no solve
+    PeerSlot* peers[ICP_MAX_PEERS];   // NVLink peer mode: exchange buffers of all ranks (mine included)
+    int peer_world, peer_rank;
 };
 
 struct InitArgs {
@@ -402,6 +407,41 @@ __global__ void __launch_bounds__(kSolveThreads) solve_kernel(const __grid_const
         }
         __syncthreads();
         if (P.mode == 1) return;
+        if (P.peer_world > 1) {
+            // ---- fused exchange over NVLink: store my sums into every rank's buffer, publish, wait
+            // for the same iteration of every peer, add in rank order (bit-identical on all ranks) ----
+            const unsigned long long seq = P.ctrl->seq + 1ull;
+            const int par = (int)(seq & 1ull);
+            if (tid < ICP_PART_STRIDE) {
+                const double v = tid < ICP_NSUMS ? sS[tid] : 0.0;
+                for (int r = 0; r < P.peer_world; r++) P.peers[r][par * ICP_MAX_PEERS + P.peer_rank].sums[tid] = v;
+                __threadfence_system();
+            }
+            __syncthreads();
+            if (tid < P.peer_world) {
+                volatile unsigned long long* flag = &P.peers[tid][par * ICP_MAX_PEERS + P.peer_rank].seq;
+                *flag = seq;
+                __threadfence_system();
+                // wait until rank `tid` has published this iteration into MY buffer
+                volatile unsigned long long* mine = &P.peers[P.peer_rank][par * ICP_MAX_PEERS + tid].seq;
+                const long long t0 = clock64();
+                while (*mine != seq) {
+                    if (clock64() - t0 > 4000000000ll) { P.ctrl->comm_error = 1; break; }   // ~2 s: never hang the GPU
+                }
+                __threadfence_system();
+            }
+            __syncthreads();
+            if (tid < ICP_NSUMS) {
+                double s = 0.0;
+                for (int r = 0; r < P.peer_world; r++) {
+                    const volatile double* src = P.peers[P.peer_rank][par * ICP_MAX_PEERS + r].sums;
+                    s += src[tid];
+                }
+                sS[tid] = s;
+            }
+            __syncthreads();
+            if (tid == 0) P.ctrl->seq = seq;
+        }
     } else {
         if (tid < ICP_NSUMS) sS[tid] = P.gsum[(size_t)seg * ICP_PART_STRIDE + tid];
         __syncthreads();
@@ -420,7 +460,8 @@ __global__ void __launch_bounds__(kSolveThreads) solve_kernel(const __grid_const
         P.trace_diff[(size_t)seg * P.trace_stride + k] = diff;
     }
     int stop = 0;
-    if (P.mode == 3) stop = 4;
+    if (P.peer_world > 1 && P.ctrl->comm_error) stop = 5;
+    else if (P.mode == 3) stop = 4;
     else if (!(diff > (double)lp.diff_threshold)) stop = 1;                                    // myicp.cpp:123
     else if (st->iter >= lp.max_iters) stop = 3;                                               // iters++ < max_iters
     else if (lp.rel_diff_tol > 0.0 && k > 0 && fabs(st->prev_diff - diff) <= lp.rel_diff_tol * st->prev_diff) stop = 2;
@@ -618,10 +659,14 @@ int icp_run_loop(icpsymm_ctx* ctx, int max_iters, float thr, const float* T_init
     sp.trace_diff = ctx->opt_trace ? ctx->trace_diff : nullptr;
     sp.blocks_per_seg = bps; sp.trace_stride = ctx->trace_stride; sp.mode = single_search ? 3 : 0;
     if (!ctx->d_ctrl) {
-        ICP_CUDA_CHECK(cudaMalloc((void**)&ctx->d_ctrl, 2 * sizeof(unsigned int)));
-        ICP_CUDA_CHECK(cudaMemsetAsync(ctx->d_ctrl, 0, 2 * sizeof(unsigned int), st));
+        ICP_CUDA_CHECK(cudaMalloc((void**)&ctx->d_ctrl, sizeof(LoopCtrl)));
+        ICP_CUDA_CHECK(cudaMemsetAsync(ctx->d_ctrl, 0, sizeof(LoopCtrl), st));
     }
     sp.ctrl = (LoopCtrl*)ctx->d_ctrl; sp.use_cond = 0; sp.cond = 0;
+    sp.peer_world = ctx->peer_world; sp.peer_rank = ctx->shard_rank;
+    for (int r = 0; r < ICP_MAX_PEERS; r++) sp.peers[r] = (PeerSlot*)ctx->peer_ptrs[r];
+    if (ctx->peer_world > 1 && nseg != 1)
+        return icp_fail_msg(ctx, ICPSYMM_ERR_INVALID, "the NVLink peer exchange supports single pairs only");
 
     const bool use_comm = ctx->nccl_comm != nullptr && ctx->shard_world > 1;
     const bool timing = ctx->opt_kernel_timing != 0;
@@ -646,7 +691,7 @@ int icp_run_loop(icpsymm_ctx* ctx, int max_iters, float thr, const float* T_init
         key.p0 = S.pts; key.p1 = T.pts; key.p2 = ctx->partial; key.p3 = ctx->corr_pos; key.p4 = ctx->d_state;
         key.p5 = ctx->opt_trace ? (const void*)ctx->trace_T : (const void*)T.nodes;
         key.shard_rank = ctx->shard_rank; key.shard_world = ctx->shard_world; key.trace = ctx->opt_trace;
-        key.comm_mode = ctx->opt_use_graph;
+        key.comm_mode = ctx->opt_use_graph + 16 * ctx->peer_world;
         // pointers of the remaining arrays change only together with the ones above (same reserve calls)
         if (!ctx->graph_exec || !(ctx->graph_key == key)) {
             if (ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }
@@ -692,6 +737,11 @@ int icp_run_loop(icpsymm_ctx* ctx, int max_iters, float thr, const float* T_init
     ICP_CUDA_CHECK(cudaMemcpyAsync(ctx->h_state, ctx->d_state, sizeof(SegState) * nseg, cudaMemcpyDeviceToHost, st));
     ICP_CUDA_CHECK(cudaStreamSynchronize(st));
     ctx->have_corr = true;
+    if (ctx->peer_world > 1) {
+        LoopCtrl hc;
+        ICP_CUDA_CHECK(cudaMemcpy(&hc, ctx->d_ctrl, sizeof hc, cudaMemcpyDeviceToHost));
+        if (hc.comm_error) return icp_fail_msg(ctx, ICPSYMM_ERR_COMM, "peer exchange timed out: a rank did not publish its sums");
+    }
 
     float loop_ms = 0.f;
     cudaEventElapsedTime(&loop_ms, ctx->ev_begin, ctx->ev_end);

@@ -98,6 +98,10 @@ struct icpsymm_ctx {
     int shard_rank = 0, shard_world = 1;
     void* nccl_comm = nullptr;
     void* nccl_lib = nullptr;
+    // NVLink peer exchange (comm.cu): my buffer + the mapped buffers of all ranks
+    void* peer_local = nullptr;
+    void* peer_ptrs[ICP_MAX_PEERS] = {nullptr};
+    int peer_world = 0;
 };
 
 int icp_fail(icpsymm_ctx* ctx, cudaError_t e, const char* expr, const char* file, int line);

@@ -82,6 +82,9 @@ def load():
         "icpsymm_comm_init": (C.c_int, [vp, vp, C.c_int, C.c_int]),
         "icpsymm_comm_destroy": (C.c_int, [vp]),
         "icpsymm_set_query_shard": (C.c_int, [vp, C.c_int, C.c_int]),
+        "icpsymm_peer_export": (C.c_int, [vp, vp]),
+        "icpsymm_peer_attach": (C.c_int, [vp, vp, C.c_int, C.c_int]),
+        "icpsymm_peer_detach": (C.c_int, [vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -312,6 +315,15 @@ class Context:
     # ---- multi-GPU ----
     def set_query_shard(self, rank, world):
         self._check(self.L.icpsymm_set_query_shard(self.h, rank, world))
+
+    def peer_export(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        self._check(self.L.icpsymm_peer_export(self.h, buf))
+        return buf.raw
+
+    def peer_attach(self, handles: bytes, world, rank):
+        buf = C.create_string_buffer(handles, 64 * world)
+        self._check(self.L.icpsymm_peer_attach(self.h, buf, world, rank))
 
     def comm_init(self, unique_id: bytes, world, rank):
         buf = C.create_string_buffer(unique_id, 128)

@@ -145,6 +145,14 @@ int icpsymm_comm_unique_id(void* id_out128);                       /* ncclGetUni
 int icpsymm_comm_init(icpsymm_ctx* ctx, const void* id128, int n_ranks, int rank);
 int icpsymm_comm_destroy(icpsymm_ctx* ctx);
 int icpsymm_set_query_shard(icpsymm_ctx* ctx, int rank, int n_ranks); /* without comm: shard only */
+/* NCCL-free exchange for the query-sharded mode: the reduce+solve kernel itself stores its 37 sums
+ * into every peer's exchange buffer over NVLink (CUDA IPC peer mapping), waits for the peers' sums
+ * of the same iteration and adds them in rank order -- one kernel, usable inside the device-side
+ * loop graph.  Each rank exports a 64-byte handle, the host application gathers the handles of all
+ * ranks (any transport) and every rank attaches with the full table.  Single pairs only. */
+int icpsymm_peer_export(icpsymm_ctx* ctx, void* handle64_out);
+int icpsymm_peer_attach(icpsymm_ctx* ctx, const void* handles /* n_ranks x 64 bytes */, int n_ranks, int rank);
+int icpsymm_peer_detach(icpsymm_ctx* ctx);
 
 #ifdef __cplusplus
 }
