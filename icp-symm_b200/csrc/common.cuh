@@ -90,6 +90,78 @@ __device__ __forceinline__ float dist2_rn(float px, float py, float pz, float qx
     return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
 }
 
+// ---- packed fp32x2 arithmetic (sm_100 FADD2 / FMUL2) ----------------------------------------
+// Two independent round-to-nearest operations per instruction: bit-identical to the scalar
+// forms, half the issue slots.  Only add and mul are used and the sums of squares stay scalar:
+// ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 (it does not do that to scalar .rn
+// code), which would break the separately-rounded contract of the distances and bounds.
+struct f32x2 {
+    unsigned long long v;
+};
+__device__ __forceinline__ f32x2 pack2(float a, float b) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 p, float& a, float& b) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(p.v));
+}
+__device__ __forceinline__ f32x2 add2_rn(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+    return r;
+}
+__device__ __forceinline__ f32x2 mul2_rn(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+    return r;
+}
+
+// negated query, packed once per query: (-qx,-qx), (-qy,-qy), (-qz,-qz) for box pairs and
+// (-qx,-qy) for points.  c + (-q) = -(q - c) exactly, and only its square is used.
+struct NegQuery {
+    f32x2 xx, yy, zz, xy;
+    float nz;
+};
+__device__ __forceinline__ NegQuery make_neg_query(float qx, float qy, float qz) {
+    NegQuery n;
+    n.xx = pack2(-qx, -qx); n.yy = pack2(-qy, -qy); n.zz = pack2(-qz, -qz);
+    n.xy = pack2(-qx, -qy);
+    n.nz = -qz;
+    return n;
+}
+
+// dist2_rn(q, c) with the x,y lanes packed: same value bit for bit
+__device__ __forceinline__ float dist2_packed(const NegQuery& nq, const float4& c) {
+    float sx, sy;
+    f32x2 d = add2_rn(pack2(c.x, c.y), nq.xy);
+    unpack2(mul2_rn(d, d), sx, sy);
+    const float dz = __fadd_rn(c.z, nq.nz);
+    return __fadd_rn(__fadd_rn(sx, sy), __fmul_rn(dz, dz));
+}
+
+// bounds of two boxes (children c, c+1 of one record) against one query, packed
+__device__ __forceinline__ void box_bounds2(float lx0, float lx1, float ly0, float ly1, float lz0, float lz1, float hx0,
+                                            float hx1, float hy0, float hy1, float hz0, float hz1, const NegQuery& nq,
+                                            uint32_t& b0, uint32_t& b1) {
+    float ax0, ax1, ay0, ay1, az0, az1, cx0, cx1, cy0, cy1, cz0, cz1;
+    unpack2(add2_rn(pack2(lx0, lx1), nq.xx), ax0, ax1);   // lo - q
+    unpack2(add2_rn(pack2(ly0, ly1), nq.yy), ay0, ay1);
+    unpack2(add2_rn(pack2(lz0, lz1), nq.zz), az0, az1);
+    unpack2(add2_rn(pack2(hx0, hx1), nq.xx), cx0, cx1);   // hi - q = -(q - hi)
+    unpack2(add2_rn(pack2(hy0, hy1), nq.yy), cy0, cy1);
+    unpack2(add2_rn(pack2(hz0, hz1), nq.zz), cz0, cz1);
+    const float ex0 = fmaxf(fmaxf(ax0, -cx0), 0.f), ex1 = fmaxf(fmaxf(ax1, -cx1), 0.f);
+    const float ey0 = fmaxf(fmaxf(ay0, -cy0), 0.f), ey1 = fmaxf(fmaxf(ay1, -cy1), 0.f);
+    const float ez0 = fmaxf(fmaxf(az0, -cz0), 0.f), ez1 = fmaxf(fmaxf(az1, -cz1), 0.f);
+    float sx0, sx1, sy0, sy1, sz0, sz1;
+    unpack2(mul2_rn(pack2(ex0, ex1), pack2(ex0, ex1)), sx0, sx1);
+    unpack2(mul2_rn(pack2(ey0, ey1), pack2(ey0, ey1)), sy0, sy1);
+    unpack2(mul2_rn(pack2(ez0, ez1), pack2(ez0, ez1)), sz0, sz1);
+    b0 = __float_as_uint(__fadd_rn(__fadd_rn(sx0, sy0), sz0));
+    b1 = __float_as_uint(__fadd_rn(__fadd_rn(sx1, sy1), sz1));
+}
+
 // lower bound of dist2_rn from (qx,qy,qz) to any point inside the box.  Same operation order as
 // dist2_rn: every step is monotone under round-to-nearest, so bound <= member distance exactly.
 __device__ __forceinline__ float box_dist2_rn(const float4& lo, const float4& hi, float qx, float qy, float qz) {

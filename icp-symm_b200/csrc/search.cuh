@@ -37,6 +37,11 @@ __device__ __forceinline__ void best_offer(Best& b, const float4& c, uint32_t po
     uint32_t id = __float_as_uint(c.w);
     if (d < b.d2 || (d == b.d2 && id < b.id)) { b.d2 = d; b.id = id; b.pos = pos; }
 }
+__device__ __forceinline__ void best_offer_packed(Best& b, const float4& c, uint32_t pos, const NegQuery& nq) {
+    float d = dist2_packed(nq, c);
+    uint32_t id = __float_as_uint(c.w);
+    if (d < b.d2 || (d == b.d2 && id < b.id)) { b.d2 = d; b.id = id; b.pos = pos; }
+}
 
 __device__ __forceinline__ void scan_leaf(const float4* __restrict__ seg_pts, uint32_t g, float qx, float qy,
                                           float qz, Best& b) {
@@ -44,8 +49,9 @@ __device__ __forceinline__ void scan_leaf(const float4* __restrict__ seg_pts, ui
     float4 c[ICP_LEAF];
 #pragma unroll
     for (int j = 0; j < ICP_LEAF; j++) c[j] = ldg4(lp + j);
+    const NegQuery nq = make_neg_query(qx, qy, qz);
 #pragma unroll
-    for (int j = 0; j < ICP_LEAF; j++) best_offer(b, c[j], g * ICP_LEAF + j, qx, qy, qz);
+    for (int j = 0; j < ICP_LEAF; j++) best_offer_packed(b, c[j], g * ICP_LEAF + j, nq);
 }
 
 // Warp-synchronous variant: the 32 lanes hold 32 neighbouring queries (consecutive points of the
@@ -109,19 +115,18 @@ __device__ __forceinline__ uint32_t warp_node_test(const WideNode* __restrict__ 
 #pragma unroll
         for (int j = 0; j < 12; j++) r[j] = ldg4(p4 + j);
         uint32_t mine = 0;
+        const NegQuery nq = make_neg_query(qx, qy, qz);
 #pragma unroll
         for (int h = 0; h < 2; h++) {
-            const float lox[4] = {r[h].x, r[h].y, r[h].z, r[h].w};
-            const float loy[4] = {r[2 + h].x, r[2 + h].y, r[2 + h].z, r[2 + h].w};
-            const float loz[4] = {r[4 + h].x, r[4 + h].y, r[4 + h].z, r[4 + h].w};
-            const float hix[4] = {r[6 + h].x, r[6 + h].y, r[6 + h].z, r[6 + h].w};
-            const float hiy[4] = {r[8 + h].x, r[8 + h].y, r[8 + h].z, r[8 + h].w};
-            const float hiz[4] = {r[10 + h].x, r[10 + h].y, r[10 + h].z, r[10 + h].w};
-#pragma unroll
-            for (int c = 0; c < 4; c++) {
-                const uint32_t lb = point_box_bits(lox[c], loy[c], loz[c], hix[c], hiy[c], hiz[c], qx, qy, qz);
-                mine |= (lb <= my_bound && lb != ICP_INF_BITS) ? (1u << (4 * h + c)) : 0u;
-            }
+            uint32_t b0, b1, b2, b3;   // children 4h .. 4h+3, two per packed evaluation
+            box_bounds2(r[h].x, r[h].y, r[2 + h].x, r[2 + h].y, r[4 + h].x, r[4 + h].y, r[6 + h].x, r[6 + h].y,
+                        r[8 + h].x, r[8 + h].y, r[10 + h].x, r[10 + h].y, nq, b0, b1);
+            box_bounds2(r[h].z, r[h].w, r[2 + h].z, r[2 + h].w, r[4 + h].z, r[4 + h].w, r[6 + h].z, r[6 + h].w,
+                        r[8 + h].z, r[8 + h].w, r[10 + h].z, r[10 + h].w, nq, b2, b3);
+            mine |= (b0 <= my_bound && b0 != ICP_INF_BITS) ? (1u << (4 * h)) : 0u;
+            mine |= (b1 <= my_bound && b1 != ICP_INF_BITS) ? (2u << (4 * h)) : 0u;
+            mine |= (b2 <= my_bound && b2 != ICP_INF_BITS) ? (4u << (4 * h)) : 0u;
+            mine |= (b3 <= my_bound && b3 != ICP_INF_BITS) ? (8u << (4 * h)) : 0u;
         }
         mask2 = __reduce_or_sync(0xffffffffu, active ? mine : 0u) & mask1;
     } else {
@@ -269,11 +274,12 @@ template <int KMAX, bool EXACT>
 __device__ __forceinline__ void knn_offer_leaf(KList<KMAX, EXACT>& L, int k, const float4* __restrict__ lp,
                                                float qx, float qy, float qz) {
     unsigned long long kk[ICP_LEAF];
+    const NegQuery nq = make_neg_query(qx, qy, qz);
 #pragma unroll
     for (int j = 0; j < ICP_LEAF; j++) {
         const float4 c = ldg4(lp + j);
         const uint32_t id = __float_as_uint(c.w);
-        const float d = dist2_rn(qx, qy, qz, c.x, c.y, c.z);
+        const float d = dist2_packed(nq, c);
         kk[j] = (id != (uint32_t)ICP_INVALID_ID) ? (((unsigned long long)__float_as_uint(d) << 32) | id) : ~0ull;
     }
     unsigned long long floor_key = 0ull;   // keys <= floor_key were handled in earlier rounds
