@@ -28,8 +28,8 @@ namespace {
 
 constexpr int kNNThreads = 256;
 constexpr int kNNWarps = kNNThreads / 32;
-constexpr int kSolveThreads = 512;
-constexpr int kSolveParts = kSolveThreads / ICP_NSUMS;  // 13
+constexpr int kSolveThreads = 1024;
+constexpr int kSolveParts = kSolveThreads / ICP_NSUMS;  // 27
 
 struct NNParams {
     CloudView src, tgt;
@@ -393,9 +393,19 @@ __global__ void __launch_bounds__(kSolveThreads) solve_kernel(const __grid_const
     if (P.mode != 2) {
         const int v = tid % ICP_NSUMS, part = tid / ICP_NSUMS;
         if (part < kSolveParts) {
+            // part p adds rows p, p+27, p+54, ... in that order; 8 loads are issued back to back so the
+            // (L2-latency) loads overlap instead of serialising with the adds
             double s = 0.0;
             const double* row = P.partial + (size_t)seg * P.blocks_per_seg * ICP_PART_STRIDE + v;
-            for (uint32_t b = part; b < P.blocks_per_seg; b += kSolveParts) s += row[(size_t)b * ICP_PART_STRIDE];
+            uint32_t b = part;
+            for (; b + 7 * kSolveParts < P.blocks_per_seg; b += 8 * kSolveParts) {
+                double x[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) x[u] = row[(size_t)(b + u * kSolveParts) * ICP_PART_STRIDE];
+#pragma unroll
+                for (int u = 0; u < 8; u++) s += x[u];
+            }
+            for (; b < P.blocks_per_seg; b += kSolveParts) s += row[(size_t)b * ICP_PART_STRIDE];
             sPart[part][v] = s;
         }
         __syncthreads();

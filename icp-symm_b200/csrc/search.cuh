@@ -88,9 +88,46 @@ __device__ __forceinline__ uint32_t point_box_bits(float lx, float ly, float lz,
     return __float_as_uint(__fadd_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)), __fmul_rn(ez, ez)));
 }
 
+// exact test of all 8 children of one record, every lane against its own query and bound: 12
+// warp-uniform 16-byte loads, packed arithmetic, no shuffles and no loop.  Returns the lane's
+// pass mask; kmin receives the lane's nearest passing child as (bound & ~7) | child.
+__device__ __forceinline__ uint32_t dense_children_test(const WideNode* __restrict__ nd, float qx, float qy, float qz,
+                                                        uint32_t my_bound, uint32_t& kmin) {
+    const float4* p4 = reinterpret_cast<const float4*>(nd);
+    float4 r[12];
+#pragma unroll
+    for (int j = 0; j < 12; j++) r[j] = ldg4(p4 + j);
+    uint32_t mine = 0;
+    kmin = 0xffffffffu;
+    const NegQuery nq = make_neg_query(qx, qy, qz);
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        uint32_t b[4];   // children 4h .. 4h+3, two per packed evaluation
+        box_bounds2(r[h].x, r[h].y, r[2 + h].x, r[2 + h].y, r[4 + h].x, r[4 + h].y, r[6 + h].x, r[6 + h].y,
+                    r[8 + h].x, r[8 + h].y, r[10 + h].x, r[10 + h].y, nq, b[0], b[1]);
+        box_bounds2(r[h].z, r[h].w, r[2 + h].z, r[2 + h].w, r[4 + h].z, r[4 + h].w, r[6 + h].z, r[6 + h].w,
+                    r[8 + h].z, r[8 + h].w, r[10 + h].z, r[10 + h].w, nq, b[2], b[3]);
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const bool pass = b[c] <= my_bound && b[c] != ICP_INF_BITS;
+            mine |= pass ? (1u << (4 * h + c)) : 0u;
+            kmin = min(kmin, pass ? ((b[c] & ~7u) | (uint32_t)(4 * h + c)) : 0xffffffffu);
+        }
+    }
+    return mine;
+}
+
+// far_mode: the bounds are much larger than the patch (first iterations of a badly aligned pair), so
+// the patch box would prune next to nothing: go straight to the exact test of all 8 children.
 __device__ __forceinline__ uint32_t warp_node_test(const WideNode* __restrict__ nd, float qx, float qy, float qz,
                                                    uint32_t my_bound, bool active, const WarpPatch& pb,
-                                                   uint32_t max_bound, int& pref) {
+                                                   uint32_t max_bound, bool far_mode, int& pref) {
+    if (far_mode) {
+        uint32_t kmin;
+        const uint32_t mine = dense_children_test(nd, qx, qy, qz, my_bound, kmin);
+        pref = (int)(__reduce_min_sync(0xffffffffu, active ? kmin : 0xffffffffu) & 7u);
+        return __reduce_or_sync(0xffffffffu, active ? mine : 0u);
+    }
     const int cl = threadIdx.x & 7;
     const float* f = reinterpret_cast<const float*>(nd);
     const float blx = __ldg(f + cl), bly = __ldg(f + 8 + cl), blz = __ldg(f + 16 + cl);
@@ -103,31 +140,13 @@ __device__ __forceinline__ uint32_t warp_node_test(const WideNode* __restrict__ 
     const uint32_t lbp = __float_as_uint(__fadd_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)), __fmul_rn(ez, ez)));
     const bool pass1 = lbp <= max_bound && lbp != ICP_INF_BITS;
     const uint32_t mask1 = __ballot_sync(0xffffffffu, pass1) & 0xffu;
-    const uint32_t kmin = __reduce_min_sync(0xffffffffu, pass1 ? ((lbp & ~7u) | (uint32_t)cl) : 0xffffffffu);
-    pref = (int)(kmin & 7u);
+    const uint32_t kmin1 = __reduce_min_sync(0xffffffffu, pass1 ? ((lbp & ~7u) | (uint32_t)cl) : 0xffffffffu);
+    pref = (int)(kmin1 & 7u);
     // stage 2: exact, per lane, only for the survivors
     uint32_t mask2 = 0;
     if (__popc(mask1) > 3) {
-        // dense case (queries far from the surface: the patch box prunes little): all 8 children at
-        // once from 12 uniform 16-byte loads, no shuffles and no loop
-        const float4* p4 = reinterpret_cast<const float4*>(nd);
-        float4 r[12];
-#pragma unroll
-        for (int j = 0; j < 12; j++) r[j] = ldg4(p4 + j);
-        uint32_t mine = 0;
-        const NegQuery nq = make_neg_query(qx, qy, qz);
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-            uint32_t b0, b1, b2, b3;   // children 4h .. 4h+3, two per packed evaluation
-            box_bounds2(r[h].x, r[h].y, r[2 + h].x, r[2 + h].y, r[4 + h].x, r[4 + h].y, r[6 + h].x, r[6 + h].y,
-                        r[8 + h].x, r[8 + h].y, r[10 + h].x, r[10 + h].y, nq, b0, b1);
-            box_bounds2(r[h].z, r[h].w, r[2 + h].z, r[2 + h].w, r[4 + h].z, r[4 + h].w, r[6 + h].z, r[6 + h].w,
-                        r[8 + h].z, r[8 + h].w, r[10 + h].z, r[10 + h].w, nq, b2, b3);
-            mine |= (b0 <= my_bound && b0 != ICP_INF_BITS) ? (1u << (4 * h)) : 0u;
-            mine |= (b1 <= my_bound && b1 != ICP_INF_BITS) ? (2u << (4 * h)) : 0u;
-            mine |= (b2 <= my_bound && b2 != ICP_INF_BITS) ? (4u << (4 * h)) : 0u;
-            mine |= (b3 <= my_bound && b3 != ICP_INF_BITS) ? (8u << (4 * h)) : 0u;
-        }
+        uint32_t kmin;
+        const uint32_t mine = dense_children_test(nd, qx, qy, qz, my_bound, kmin);
         mask2 = __reduce_or_sync(0xffffffffu, active ? mine : 0u) & mask1;
     } else {
         for (uint32_t mm = mask1; mm; mm &= mm - 1) {
@@ -162,12 +181,16 @@ __device__ __forceinline__ void wide_traverse_warp(const TreeShape& sh, const Wi
     pb.lox = warp_min_f(active ? qx : inf);  pb.loy = warp_min_f(active ? qy : inf);  pb.loz = warp_min_f(active ? qz : inf);
     pb.hix = warp_max_f(active ? qx : -inf); pb.hiy = warp_max_f(active ? qy : -inf); pb.hiz = warp_max_f(active ? qz : -inf);
     uint32_t max_bound = __reduce_max_sync(0xffffffffu, active ? v.bound_bits() : 0u);
+    // far mode while the largest bound exceeds 4x the squared patch diagonal (both warp-uniform)
+    const float pdx = pb.hix - pb.lox, pdy = pb.hiy - pb.loy, pdz = pb.hiz - pb.loz;
+    const uint32_t far_thr = __float_as_uint(4.f * (pdx * pdx + pdy * pdy + pdz * pdz));
+    bool far_mode = max_bound > far_thr;
     uint32_t stale = 0;   // bit l: the pending mask of level l predates the latest bound improvement
     int l = top, pref;
     uint32_t i = 0;
     unsigned long long masks =
         (unsigned long long)warp_node_test(seg_nodes + sh.level_off[top], qx, qy, qz, v.bound_bits(), active, pb,
-                                           max_bound, pref) << (8 * (top - 1));
+                                           max_bound, far_mode, pref) << (8 * (top - 1));
     for (;;) {
         const int sh8 = 8 * (l - 1);
         const uint32_t m = (uint32_t)(masks >> sh8) & 0xffu;
@@ -190,11 +213,12 @@ __device__ __forceinline__ void wide_traverse_warp(const TreeShape& sh, const Wi
             if (__any_sync(0xffffffffu, active && after != before)) {
                 stale = 0xffffffffu;
                 max_bound = __reduce_max_sync(0xffffffffu, active ? after : 0u);
+                far_mode = max_bound > far_thr;
             }
         } else {
             --l; i = child;
             const uint32_t cm = warp_node_test(seg_nodes + sh.level_off[l] + i, qx, qy, qz, v.bound_bits(), active, pb,
-                                               max_bound, pref);
+                                               max_bound, far_mode, pref);
             masks |= (unsigned long long)cm << (8 * (l - 1));
             stale &= ~(1u << l);
         }
