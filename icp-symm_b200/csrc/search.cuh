@@ -291,9 +291,9 @@ struct KList {
 };
 
 // offer the 8 points of one leaf group.  The 8 keys are formed first; then, round by round, every
-// lane inserts its smallest still-unseen key that beats its k-th best.  The number of rounds is the
-// largest number of insertions any lane needs (usually 0-2), so the long insertion body is executed
-// that many times per leaf instead of up to 8 times, and it exists once in the instruction stream.
+// lane inserts one of its keys that beat its k-th best.  The number of rounds is the largest number
+// of candidates any lane has (usually 0-2), so the long insertion body is executed that many times
+// per leaf instead of up to 8 times, and it exists once in the instruction stream.
 template <int KMAX, bool EXACT>
 __device__ __forceinline__ void knn_offer_leaf(KList<KMAX, EXACT>& L, int k, const float4* __restrict__ lp,
                                                float qx, float qy, float qz) {
@@ -306,21 +306,19 @@ __device__ __forceinline__ void knn_offer_leaf(KList<KMAX, EXACT>& L, int k, con
         const float d = dist2_packed(nq, c);
         kk[j] = (id != (uint32_t)ICP_INVALID_ID) ? (((unsigned long long)__float_as_uint(d) << 32) | id) : ~0ull;
     }
-    unsigned long long floor_key = 0ull;   // keys <= floor_key were handled in earlier rounds
-    bool first = true;
-#pragma unroll 1
-    for (;;) {
-        unsigned long long best = ~0ull;
+    // candidates that beat the current k-th best (it only decreases, so the others never will)
+    uint32_t m = 0;
 #pragma unroll
-        for (int j = 0; j < ICP_LEAF; j++) {
-            const bool fresh = first || kk[j] > floor_key;
-            best = (fresh && kk[j] < best) ? kk[j] : best;
-        }
-        const bool go = best < L.kth;
-        if (!__any_sync(0xffffffffu, go)) break;
-        if (go) L.insert(k, best);
-        floor_key = best;
-        first = false;
+    for (int j = 0; j < ICP_LEAF; j++) m |= (kk[j] < L.kth) ? (1u << j) : 0u;
+#pragma unroll 1
+    while (__any_sync(0xffffffffu, m != 0u)) {
+        // this lane's next candidate: lowest set bit (the order of insertion does not matter)
+        const uint32_t low = m & (0u - m);
+        unsigned long long cand = ~0ull;
+#pragma unroll
+        for (int j = 0; j < ICP_LEAF; j++) cand = (low == (1u << j)) ? kk[j] : cand;
+        m ^= low;
+        if (cand < L.kth) L.insert(k, cand);
     }
 }
 
