@@ -71,7 +71,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -223,7 +223,6 @@ def main():
         iters.append(st["iters"])
         launches += 2 + 2 * st["searches"]   # set_lp + init_state, then [search, solve] per WHILE-body trip
     barrier()
-    clocks = sampler.stop()
     my_ms = float(np.sum(loop_ms))
     my_corr = float(n) * float(np.sum(iters))
 
@@ -253,6 +252,7 @@ def main():
         e2e_ms.append(ev0.elapsed_time(ev1))
         e2e_iters.append(st["iters"])
     barrier()
+    clocks = sampler.stop()     # sampled across the value, roofline and e2e timed regions
     my_e2e_ms = float(np.sum(e2e_ms))
     my_e2e_corr = float(n) * float(np.sum(e2e_iters))
 
