@@ -479,3 +479,53 @@ def test_device_resident_inputs_on_caller_stream(cat, cat_out):
         assert np.array_equal(T0, T) and st0["iters"] == 5
     finally:
         c0.close()
+
+
+@pytest.mark.parametrize("case", ["identical", "line", "two_clusters", "huge_offset", "tiny_scale", "grid_plane", "mixed_scales"])
+def test_nn_degenerate_distributions(ctx, case):
+    """edge distributions for the implicit hierarchy: every one must stay bit-exact against brute force"""
+    rng = np.random.default_rng(hash(case) % 2**32)
+    n, m = 3000, 5000
+    if case == "identical":                       # all target points coincide: every index ties -> index 0
+        tgt = np.tile(np.float32([1.5, -2.0, 0.25]), (m, 1)); src = rng.standard_normal((n, 3)).astype(np.float32)
+    elif case == "line":                          # zero extent in two axes
+        tgt = np.c_[np.linspace(-5, 5, m), np.zeros(m), np.zeros(m)].astype(np.float32)
+        src = np.c_[rng.uniform(-6, 6, n), rng.normal(0, .1, n), rng.normal(0, .1, n)].astype(np.float32)
+    elif case == "two_clusters":
+        tgt = np.concatenate([rng.normal(0, 1e-3, (m // 2, 3)), rng.normal(0, 1e-3, (m - m // 2, 3)) + 1000.0]).astype(np.float32)
+        src = np.concatenate([rng.normal(0, 1.0, (n // 2, 3)), rng.normal(0, 1.0, (n - n // 2, 3)) + 1000.0]).astype(np.float32)
+    elif case == "huge_offset":                   # fp32 spacing at 1e6 is 0.06: many exact ties
+        tgt = (rng.uniform(0, 50, (m, 3)) + 1e6).astype(np.float32); src = (rng.uniform(0, 50, (n, 3)) + 1e6).astype(np.float32)
+    elif case == "tiny_scale":
+        tgt = (rng.standard_normal((m, 3)) * 1e-12).astype(np.float32); src = (rng.standard_normal((n, 3)) * 1e-12).astype(np.float32)
+    elif case == "grid_plane":                    # integer lattice in a plane: equidistant neighbours everywhere
+        g = np.stack(np.meshgrid(np.arange(70), np.arange(70), indexing="ij"), -1).reshape(-1, 2)
+        tgt = np.c_[g, np.zeros(len(g))].astype(np.float32)
+        src = np.c_[rng.integers(0, 139, (n, 2)) * 0.5, rng.integers(-2, 3, n)].astype(np.float32)
+    else:                                         # a dense blob inside a sparse shell
+        tgt = np.concatenate([rng.normal(0, 1e-4, (m // 2, 3)), rng.normal(0, 100.0, (m - m // 2, 3))]).astype(np.float32)
+        src = np.concatenate([rng.normal(0, 1e-3, (n // 2, 3)), rng.normal(0, 150.0, (n - n // 2, 3))]).astype(np.float32)
+    idx, _ = _check_nn(ctx, src, tgt)
+    if case == "identical":
+        assert (idx == 0).all()
+    # the same clouds must also survive normal estimation and a registration without NaNs
+    ctx.estimate_normals(10)
+    assert np.isfinite(ctx.get_normals(0)).all() and np.isfinite(ctx.get_normals(1)).all()
+    T, st, rc = ctx.register_symm(3, 0.0)
+    assert np.isfinite(T).all() and np.isfinite(st["diff"])
+
+
+def test_normals_knn_ties_by_lowest_index(ctx):
+    """lattice cloud: the 10th neighbour is one of many equidistant points; the kNN set must follow the oracle's
+    (d2, index) order, so the covariance and hence the normal agree wherever the spectrum is not degenerate"""
+    g = np.stack(np.meshgrid(np.arange(40), np.arange(40), indexing="ij"), -1).reshape(-1, 2)
+    P = np.c_[g, 0.01 * (g[:, 0] % 3)].astype(np.float32)
+    P = P[np.random.default_rng(3).permutation(len(P))]
+    ctx.set_source(P); ctx.set_target(P)
+    ctx.estimate_normals(10, viewpoint=(0, 0, 100))
+    dn = ctx.get_normals(0)
+    on, gap = orc.estimate_normals(P, 10, viewpoint=(0, 0, 100))
+    ok = gap > 1e-3
+    assert ok.mean() > 0.5
+    assert _angle(dn[ok, :3], on[ok, :3]).max() < 1e-4
+    assert np.allclose(dn[ok, 3], on[ok, 3], atol=2e-5)
