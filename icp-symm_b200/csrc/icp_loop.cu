@@ -140,10 +140,10 @@ __global__ void __launch_bounds__(kNNThreads, 4) nn_accum_kernel(const __grid_co
             p = apply_rn(sT, s.x, s.y, s.z);
             if (lp.identity_pairs) {
                 uint32_t pos = P.tgt.pos_of_orig[(size_t)seg * P.tgt.shape.pitch + __float_as_uint(s.w)];
-                best_offer(b, ldg4(tpts + pos), pos, p.x, p.y, p.z);
+                best_offer(b, ldg4(tpts + pos), p.x, p.y, p.z);
             } else {
                 uint32_t prev = lp.warm_start ? corr[i] : 0xffffffffu;
-                if (prev < nt) best_offer(b, ldg4(tpts + prev), prev, p.x, p.y, p.z);
+                if (prev < nt) best_offer(b, ldg4(tpts + prev), p.x, p.y, p.z);
             }
         }
         // warp-synchronous exact search: the 32 lanes are 32 neighbouring source points
@@ -152,15 +152,20 @@ __global__ void __launch_bounds__(kNNThreads, 4) nn_accum_kernel(const __grid_co
 #pragma unroll
         for (int k = 0; k < ICP_NSUMS; k++) v[k] = 0.f;
         if (active) {
-            corr[i] = b.pos;
-            if (b.pos < nt) {
-                const float4 q = ldg4(tpts + b.pos);
-                const float4 nq = ldg4(tnrm + b.pos);
+            // the key carries the original index; the sorted position comes from the inverse permutation
+            const uint32_t bpos = (b.id() != (uint32_t)ICP_INVALID_ID)
+                                      ? __ldg(P.tgt.pos_of_orig + (size_t)seg * P.tgt.shape.pitch + b.id())
+                                      : 0xffffffffu;
+            const float bd2 = b.d2();
+            corr[i] = bpos;
+            if (bpos < nt) {
+                const float4 q = ldg4(tpts + bpos);
+                const float4 nq = ldg4(tnrm + bpos);
                 const float4 n0 = ldg4(snrm + i);
                 const float3 np = rotate_rn(sT, n0.x, n0.y, n0.z);
-                v[33] = __fsqrt_rn(b.d2);
-                v[34] = b.d2;
-                if (b.d2 <= lp.max_pair_d2) {
+                v[33] = __fsqrt_rn(bd2);
+                v[34] = bd2;
+                if (bd2 <= lp.max_pair_d2) {
                     const float nx = np.x + nq.x, ny = np.y + nq.y, nz = np.z + nq.z;
                     const float ppx = p.x - sO[0], ppy = p.y - sO[1], ppz = p.z - sO[2];
                     const float qqx = q.x - sO[0], qqy = q.y - sO[1], qqz = q.z - sO[2];

@@ -20,27 +20,28 @@
 
 #define ICP_INF_BITS 0x7f800000u
 
+// best candidate so far as ONE 64-bit key, (d2 bits << 32) | original index: d2 >= 0, so unsigned
+// integer order on the key is exactly the (d2, lowest original index) order the oracle defines, and
+// an update is a 64-bit min (two compares, two selects) instead of a three-way predicate.
 struct Best {
-    float d2;
-    uint32_t id;   // original index of the best candidate
-    uint32_t pos;  // its sorted position inside the segment
+    unsigned long long key;
+    __device__ __forceinline__ float d2() const { return __uint_as_float((uint32_t)(key >> 32)); }
+    __device__ __forceinline__ uint32_t id() const { return (uint32_t)key; }
 };
 
 __device__ __forceinline__ void best_init(Best& b) {
-    b.d2 = __uint_as_float(ICP_INF_BITS);
-    b.id = ICP_INVALID_ID;
-    b.pos = 0xffffffffu;
+    b.key = ((unsigned long long)ICP_INF_BITS << 32) | (unsigned long long)ICP_INVALID_ID;
 }
 
-__device__ __forceinline__ void best_offer(Best& b, const float4& c, uint32_t pos, float qx, float qy, float qz) {
-    float d = dist2_rn(qx, qy, qz, c.x, c.y, c.z);
-    uint32_t id = __float_as_uint(c.w);
-    if (d < b.d2 || (d == b.d2 && id < b.id)) { b.d2 = d; b.id = id; b.pos = pos; }
+__device__ __forceinline__ void best_offer(Best& b, const float4& c, float qx, float qy, float qz) {
+    const float d = dist2_rn(qx, qy, qz, c.x, c.y, c.z);
+    const unsigned long long k = ((unsigned long long)__float_as_uint(d) << 32) | __float_as_uint(c.w);
+    b.key = k < b.key ? k : b.key;
 }
-__device__ __forceinline__ void best_offer_packed(Best& b, const float4& c, uint32_t pos, const NegQuery& nq) {
-    float d = dist2_packed(nq, c);
-    uint32_t id = __float_as_uint(c.w);
-    if (d < b.d2 || (d == b.d2 && id < b.id)) { b.d2 = d; b.id = id; b.pos = pos; }
+__device__ __forceinline__ void best_offer_packed(Best& b, const float4& c, const NegQuery& nq) {
+    const float d = dist2_packed(nq, c);
+    const unsigned long long k = ((unsigned long long)__float_as_uint(d) << 32) | __float_as_uint(c.w);
+    b.key = k < b.key ? k : b.key;
 }
 
 __device__ __forceinline__ void scan_leaf(const float4* __restrict__ seg_pts, uint32_t g, float qx, float qy,
@@ -51,7 +52,7 @@ __device__ __forceinline__ void scan_leaf(const float4* __restrict__ seg_pts, ui
     for (int j = 0; j < ICP_LEAF; j++) c[j] = ldg4(lp + j);
     const NegQuery nq = make_neg_query(qx, qy, qz);
 #pragma unroll
-    for (int j = 0; j < ICP_LEAF; j++) best_offer_packed(b, c[j], g * ICP_LEAF + j, nq);
+    for (int j = 0; j < ICP_LEAF; j++) best_offer_packed(b, c[j], nq);
 }
 
 // Warp-synchronous variant: the 32 lanes hold 32 neighbouring queries (consecutive points of the
@@ -229,7 +230,7 @@ struct NNVisitor {
     Best& b;
     const float4* __restrict__ pts;
     float qx, qy, qz;
-    __device__ __forceinline__ uint32_t bound_bits() const { return __float_as_uint(b.d2); }
+    __device__ __forceinline__ uint32_t bound_bits() const { return (uint32_t)(b.key >> 32); }
     __device__ __forceinline__ void leaf(uint32_t g) { scan_leaf(pts, g, qx, qy, qz, b); }
 };
 
