@@ -55,8 +55,9 @@ __global__ void __launch_bounds__(128) normals_kernel(const __grid_constant__ No
     const int k = P.k;
 
     // first bound: the query's own leaf group and its neighbours along the curve
+    __shared__ unsigned long long s_park[ICP_KNN_BUF][128];   // [slot][thread]: conflict-free columns
     KList<KMAX, EXACT> L;
-    L.init();
+    L.init(&s_park[0][threadIdx.x], 128);
     const uint32_t n_groups = pitch / ICP_LEAF;
     const uint32_t g = active ? i / ICP_LEAF : 0u, w = (k <= 16) ? 1u : 2u;
     const uint32_t g_lo = g >= w ? g - w : 0u, g_hi = (g + w < n_groups) ? g + w : n_groups - 1;
@@ -72,6 +73,7 @@ __global__ void __launch_bounds__(128) normals_kernel(const __grid_constant__ No
                 if (!mine) L.kth = 0ull;
                 knn_offer_leaf(L, k, pts + (size_t)gg * ICP_LEAF, q.x, q.y, q.z);
                 if (!mine) L.kth = saved;
+                L.maybe_flush(k);
             }
         }
     }

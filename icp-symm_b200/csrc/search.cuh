@@ -19,6 +19,7 @@
 #include "common.cuh"
 
 #define ICP_INF_BITS 0x7f800000u
+#define ICP_KNN_BUF 24                   // parked kNN candidates per lane (shared memory, 8 B each)
 
 // best candidate so far as ONE 64-bit key, (d2 bits << 32) | original index: d2 >= 0, so unsigned
 // integer order on the key is exactly the (d2, lowest original index) order the oracle defines, and
@@ -251,11 +252,30 @@ template <int KMAX, bool EXACT>
 struct KList {
     unsigned long long key[KMAX];
     unsigned long long kth;  // key[k-1]: the current k-th best
+    // candidates that beat kth are first parked in a per-lane shared-memory column and merged into
+    // the list in bursts (flush): the long insertion body then runs max-over-lanes(count) times per
+    // burst with most lanes busy, instead of once per candidate with one or two lanes busy
+    unsigned long long* buf;   // this lane's column: buf[slot * stride]
+    int stride, cnt;
 
-    __device__ __forceinline__ void init() {
+    __device__ __forceinline__ void init(unsigned long long* column, int column_stride) {
 #pragma unroll
         for (int j = 0; j < KMAX; j++) key[j] = ~0ull;
         kth = ~0ull;
+        buf = column; stride = column_stride; cnt = 0;
+    }
+    __device__ __forceinline__ void flush(int k) {
+        const int rounds = __reduce_max_sync(0xffffffffu, cnt);
+#pragma unroll 1
+        for (int r = 0; r < rounds; r++) {
+            const unsigned long long cand = (r < cnt) ? buf[r * stride] : ~0ull;
+            if (cand < kth) insert(k, cand);
+        }
+        cnt = 0;
+    }
+    // merge when some lane has no room left for another leaf group
+    __device__ __forceinline__ void maybe_flush(int k) {
+        if (__any_sync(0xffffffffu, cnt > ICP_KNN_BUF - ICP_LEAF)) flush(k);
     }
     // sorted insert of a key that is known to be < kth: slot j keeps its key while it is smaller
     // than the new one, otherwise it takes the new key (first such slot) or its left neighbour
@@ -291,10 +311,9 @@ struct KList {
     __device__ __forceinline__ uint32_t bound_bits() const { return (uint32_t)(kth >> 32); }
 };
 
-// offer the 8 points of one leaf group.  The 8 keys are formed first; then, round by round, every
-// lane inserts one of its keys that beat its k-th best.  The number of rounds is the largest number
-// of candidates any lane has (usually 0-2), so the long insertion body is executed that many times
-// per leaf instead of up to 8 times, and it exists once in the instruction stream.
+// offer the 8 points of one leaf group: form the 8 keys and park the ones that beat the lane's current
+// k-th best; the caller merges (maybe_flush) when a lane's column is nearly full.  Until the merge the pruning bound is the
+// (slightly stale, hence only looser) k-th best of the last merge: exactness is unaffected.
 template <int KMAX, bool EXACT>
 __device__ __forceinline__ void knn_offer_leaf(KList<KMAX, EXACT>& L, int k, const float4* __restrict__ lp,
                                                float qx, float qy, float qz) {
@@ -307,19 +326,10 @@ __device__ __forceinline__ void knn_offer_leaf(KList<KMAX, EXACT>& L, int k, con
         const float d = dist2_packed(nq, c);
         kk[j] = (id != (uint32_t)ICP_INVALID_ID) ? (((unsigned long long)__float_as_uint(d) << 32) | id) : ~0ull;
     }
-    // candidates that beat the current k-th best (it only decreases, so the others never will)
-    uint32_t m = 0;
+    // park the candidates that beat the current k-th best (warp-uniform call: every lane runs this)
 #pragma unroll
-    for (int j = 0; j < ICP_LEAF; j++) m |= (kk[j] < L.kth) ? (1u << j) : 0u;
-#pragma unroll 1
-    while (__any_sync(0xffffffffu, m != 0u)) {
-        // this lane's next candidate: lowest set bit (the order of insertion does not matter)
-        const uint32_t low = m & (0u - m);
-        unsigned long long cand = ~0ull;
-#pragma unroll
-        for (int j = 0; j < ICP_LEAF; j++) cand = (low == (1u << j)) ? kk[j] : cand;
-        m ^= low;
-        if (cand < L.kth) L.insert(k, cand);
+    for (int j = 0; j < ICP_LEAF; j++) {
+        if (kk[j] < L.kth) { L.buf[L.cnt * L.stride] = kk[j]; L.cnt++; }
     }
 }
 
@@ -342,6 +352,7 @@ struct KnnVisitor {
         if (skip) L.kth = 0ull;                 // nothing beats 0: no insertion for this lane
         knn_offer_leaf(L, k, pts + (size_t)g * ICP_LEAF, qx, qy, qz);
         if (skip) L.kth = saved;
+        L.maybe_flush(k);
     }
 };
 
@@ -351,5 +362,7 @@ __device__ __forceinline__ void knn_traverse_warp(const TreeShape& sh, const Wid
                                                   int k, uint32_t g_lo, uint32_t g_hi, bool active,
                                                   KList<KMAX, EXACT>& L) {
     KnnVisitor<KMAX, EXACT> v{L, seg_pts, qx, qy, qz, k, g_lo, g_hi, active};
+    L.flush(k);                                   // the caller's window scan
     wide_traverse_warp(sh, seg_nodes, qx, qy, qz, active, v);
+    L.flush(k);
 }
