@@ -19,7 +19,7 @@
 #include "common.cuh"
 
 #define ICP_INF_BITS 0x7f800000u
-#define ICP_KNN_BUF 24                   // parked kNN candidates per lane (shared memory, 8 B each)
+#define ICP_KNN_BUF 32                   // parked kNN candidates per lane (shared memory, 8 B each)
 
 // best candidate so far as ONE 64-bit key, (d2 bits << 32) | original index: d2 >= 0, so unsigned
 // integer order on the key is exactly the (d2, lowest original index) order the oracle defines, and
