@@ -188,6 +188,7 @@ def main():
     h_tgt = torch.from_numpy(tgt).pin_memory()
     ctx = icp.Context(local_rank)
     ctx.set_option(icp.OPT_REL_DIFF_TOL, REL_TOL)
+    ctx.set_option(icp.OPT_ASYNC_SETUP, 1)      # per-cloud streams: the target's H2D overlaps the source's build
     stream = torch.cuda.ExternalStream(ctx.stream, device=local_rank)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")   # > 126 MB L2
 

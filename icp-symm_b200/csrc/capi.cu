@@ -80,14 +80,23 @@ int icpsymm_create(icpsymm_ctx** out, int device) {
 void icpsymm_destroy(icpsymm_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    icp_join_clouds(ctx, false);
     cudaStreamSynchronize(ctx->stream);
     icpsymm_comm_destroy(ctx);
     icpsymm_peer_detach(ctx);
     if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
     icp_free_cloudset(ctx->src);
     icp_free_cloudset(ctx->tgt);
-    cudaFree(ctx->staging); cudaFree(ctx->keys_a); cudaFree(ctx->keys_b); cudaFree(ctx->vals_a); cudaFree(ctx->vals_b);
-    cudaFree(ctx->cub_temp); cudaFree(ctx->d_flags); cudaFree(ctx->d_state); cudaFree(ctx->d_lp); cudaFree(ctx->d_ctrl);
+    for (int k = 0; k < 2; k++) {
+        if (ctx->aux[k]) { cudaStreamSynchronize(ctx->aux[k]); cudaStreamDestroy(ctx->aux[k]); }
+        if (ctx->ready[k]) cudaEventDestroy(ctx->ready[k]);
+        BuildScratch& B = ctx->scratch[k];
+        cudaFree(B.staging); cudaFree(B.keys_a); cudaFree(B.keys_b); cudaFree(B.vals_a); cudaFree(B.vals_b);
+        cudaFree(B.cub_temp); cudaFree(B.d_flags);
+        if (B.h_flag) cudaFreeHost(B.h_flag);
+    }
+    if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
+    cudaFree(ctx->d_state); cudaFree(ctx->d_lp); cudaFree(ctx->d_ctrl);
     cudaFree(ctx->corr_pos); cudaFree(ctx->partial); cudaFree(ctx->gsum); cudaFree(ctx->trace_T);
     cudaFree(ctx->trace_diff); cudaFree(ctx->io_buf);
     if (ctx->h_state) cudaFreeHost(ctx->h_state);
@@ -104,6 +113,7 @@ void* icpsymm_get_stream(const icpsymm_ctx* ctx) { return ctx ? (void*)ctx->stre
 
 int icpsymm_synchronize(icpsymm_ctx* ctx) {
     if (!ctx) return ICPSYMM_ERR_INVALID;
+    { int jr = icp_join_clouds(ctx, true); if (jr < 0) return jr; }
     ICP_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     return ICPSYMM_OK;
 }
@@ -119,6 +129,12 @@ int icpsymm_set_option(icpsymm_ctx* ctx, int key, double value) {
         case ICPSYMM_OPT_WARM_START: ctx->opt_warm_start = value != 0; break;
         case ICPSYMM_OPT_TRACE: ctx->opt_trace = value != 0; break;
         case ICPSYMM_OPT_GRID_BLOCKS: if (value < 0) return ICPSYMM_ERR_INVALID; ctx->opt_grid_blocks = (int)value; break;
+        case ICPSYMM_OPT_ASYNC_SETUP: {
+            int jr = icp_join_clouds(ctx, true);   // never switch modes with work in flight
+            ctx->opt_async_setup = value != 0;
+            if (jr < 0) return jr;
+            break;
+        }
         default: return icp_fail_msg(ctx, ICPSYMM_ERR_INVALID, "unknown option key");
     }
     return ICPSYMM_OK;
@@ -129,6 +145,7 @@ static int set_cloud(icpsymm_ctx* ctx, CloudSet& cs, const float* xyz, bool dev,
     if (!ctx) return ICPSYMM_ERR_INVALID;
     if (cudaSetDevice(ctx->device) != cudaSuccess) return icp_fail_msg(ctx, ICPSYMM_ERR_CUDA, "cudaSetDevice");
     ctx->have_corr = false;
+    cs.slot = (&cs == &ctx->tgt) ? 1 : 0;
     return icp_build_cloudset(ctx, cs, xyz, dev, counts, nseg, max_count, stride);
 }
 
@@ -160,7 +177,7 @@ int icpsymm_estimate_normals(icpsymm_ctx* ctx, int k, const float viewpoint[3]) 
     if (rc) return rc;
     rc = icp_estimate_normals(ctx, ctx->tgt, k, viewpoint);
     if (rc) return rc;
-    ICP_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    if (!ctx->opt_async_setup) ICP_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     return ICPSYMM_OK;
 }
 

@@ -602,6 +602,7 @@ int icp_run_loop(icpsymm_ctx* ctx, int max_iters, float thr, const float* T_init
                  bool single_search, float* T_out, icpsymm_stats* stats) {
     CloudSet& S = ctx->src;
     CloudSet& T = ctx->tgt;
+    { int jr = icp_join_clouds(ctx, true); if (jr < 0) return jr; }   // asynchronous setup: join + deferred checks
     if (!S.valid || !T.valid) return icp_fail_msg(ctx, ICPSYMM_ERR_NOT_READY, "set_source / set_target first");
     if (S.nseg != T.nseg) return icp_fail_msg(ctx, ICPSYMM_ERR_SIZE, "source and target hold a different number of pairs");
     if (max_iters < 0) return icp_fail_msg(ctx, ICPSYMM_ERR_INVALID, "max_iters < 0");
@@ -831,6 +832,7 @@ int icp_export_correspondences(icpsymm_ctx* ctx, int32_t* idx_out, float* d2_out
 
 int icp_export_transformed(icpsymm_ctx* ctx, const float* T, float* xyz_out, size_t stride_bytes) {
     CloudSet& S = ctx->src;
+    { int jr = icp_join_clouds(ctx, true); if (jr < 0) return jr; }
     if (!S.valid) return icp_fail_msg(ctx, ICPSYMM_ERR_NOT_READY, "set_source first");
     if (!T || !xyz_out || stride_bytes < 12 || (stride_bytes & 3)) return icp_fail_msg(ctx, ICPSYMM_ERR_INVALID, "bad argument");
     size_t n = (size_t)S.nseg * S.max_count;

@@ -221,6 +221,46 @@ template int icp_reserve<float>(icpsymm_ctx*, float**, size_t*, size_t);
 template int icp_reserve<char>(icpsymm_ctx*, char**, size_t*, size_t);
 template int icp_reserve<SegState>(icpsymm_ctx*, SegState**, size_t*, size_t);
 
+cudaStream_t icp_cloud_stream(icpsymm_ctx* ctx, CloudSet& cs) {
+    if (!ctx->opt_async_setup) return ctx->stream;
+    const int k = cs.slot;
+    if (!ctx->aux[k]) {
+        if (cudaStreamCreateWithFlags(&ctx->aux[k], cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); return ctx->stream; }
+        cudaEventCreateWithFlags(&ctx->ready[k], cudaEventDisableTiming);
+    }
+    if (!ctx->fork_ev) cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming);
+    // order after everything already enqueued on the context stream (it may still read this cloud)
+    cudaEventRecord(ctx->fork_ev, ctx->stream);
+    cudaStreamWaitEvent(ctx->aux[k], ctx->fork_ev, 0);
+    return ctx->aux[k];
+}
+
+void icp_cloud_done(icpsymm_ctx* ctx, CloudSet& cs) {
+    if (!ctx->opt_async_setup || !ctx->aux[cs.slot]) return;
+    cudaEventRecord(ctx->ready[cs.slot], ctx->aux[cs.slot]);
+    cs.on_aux = true;
+}
+
+int icp_join_clouds(icpsymm_ctx* ctx, bool check) {
+    CloudSet* both[2] = {&ctx->src, &ctx->tgt};
+    int rc = ICPSYMM_OK;
+    for (CloudSet* cs : both) {
+        if (cs->on_aux) {
+            cudaStreamWaitEvent(ctx->stream, ctx->ready[cs->slot], 0);
+            cs->on_aux = false;
+        }
+        if (check && cs->pending_check) {
+            cs->pending_check = false;
+            cudaEventSynchronize(ctx->ready[cs->slot]);
+            if (ctx->scratch[cs->slot].h_flag && *ctx->scratch[cs->slot].h_flag) {
+                cs->valid = false;
+                rc = icp_fail_msg(ctx, ICPSYMM_ERR_NONFINITE, "cloud holds NaN/Inf coordinates");
+            }
+        }
+    }
+    return rc;
+}
+
 TreeShape icp_make_shape(uint32_t max_count) {
     TreeShape sh;
     memset(&sh, 0, sizeof sh);
@@ -254,8 +294,9 @@ int icp_build_cloudset(icpsymm_ctx* ctx, CloudSet& cs, const float* xyz, bool on
     if (!xyz || nseg == 0 || max_count == 0) return icp_fail_msg(ctx, ICPSYMM_ERR_INVALID, "empty cloud");
     if (stride_bytes < 12 || (stride_bytes & 3)) return icp_fail_msg(ctx, ICPSYMM_ERR_INVALID, "stride_bytes must be >= 12 and a multiple of 4");
     if (max_count > 0x7ffffff0ull || nseg > 0x100000ull) return icp_fail_msg(ctx, ICPSYMM_ERR_INVALID, "cloud too large");
-    cudaStream_t st = ctx->stream;
-    cs.valid = false; cs.has_normals = false;
+    cudaStream_t st = icp_cloud_stream(ctx, cs);
+    BuildScratch& B = ctx->scratch[cs.slot];
+    cs.valid = false; cs.has_normals = false; cs.pending_check = false;
     TreeShape sh = icp_make_shape((uint32_t)max_count);
     if (sh.n_levels == 0) return icp_fail_msg(ctx, ICPSYMM_ERR_INVALID, "cloud too large for the 8-level hierarchy");
     size_t slots = nseg * (size_t)sh.pitch, nodes = nseg * (size_t)sh.nodes_per_seg;
@@ -282,52 +323,53 @@ int icp_build_cloudset(icpsymm_ctx* ctx, CloudSet& cs, const float* xyz, bool on
     cap = cs.cap_seg;  if ((rc = icp_reserve(ctx, &cs.bb_lo, &cap, nseg))) return rc;
     cap = cs.cap_seg;  if ((rc = icp_reserve(ctx, &cs.bb_hi, &cap, nseg))) return rc;
     cs.cap_seg = cap;
-    cap = ctx->sort_cap; if ((rc = icp_reserve(ctx, &ctx->keys_a, &cap, slots))) return rc;
-    cap = ctx->sort_cap; if ((rc = icp_reserve(ctx, &ctx->keys_b, &cap, slots))) return rc;
-    cap = ctx->sort_cap; if ((rc = icp_reserve(ctx, &ctx->vals_a, &cap, slots))) return rc;
-    cap = ctx->sort_cap; if ((rc = icp_reserve(ctx, &ctx->vals_b, &cap, slots))) return rc;
-    ctx->sort_cap = cap;
-    if (!ctx->d_flags) ICP_CUDA_CHECK(cudaMalloc((void**)&ctx->d_flags, 4 * sizeof(int)));
+    cap = B.sort_cap; if ((rc = icp_reserve(ctx, &B.keys_a, &cap, slots))) return rc;
+    cap = B.sort_cap; if ((rc = icp_reserve(ctx, &B.keys_b, &cap, slots))) return rc;
+    cap = B.sort_cap; if ((rc = icp_reserve(ctx, &B.vals_a, &cap, slots))) return rc;
+    cap = B.sort_cap; if ((rc = icp_reserve(ctx, &B.vals_b, &cap, slots))) return rc;
+    B.sort_cap = cap;
+    if (!B.d_flags) ICP_CUDA_CHECK(cudaMalloc((void**)&B.d_flags, 4 * sizeof(int)));
+    if (!B.h_flag) ICP_CUDA_CHECK(cudaMallocHost((void**)&B.h_flag, sizeof(int)));
 
     const char* raw = reinterpret_cast<const char*>(xyz);
     if (!on_device) {
         size_t bytes = nseg * max_count * stride_bytes;
-        char* stg = (char*)ctx->staging;
-        if ((rc = icp_reserve(ctx, &stg, &ctx->staging_bytes, bytes))) return rc;
-        ctx->staging = stg;
+        char* stg = (char*)B.staging;
+        if ((rc = icp_reserve(ctx, &stg, &B.staging_bytes, bytes))) return rc;
+        B.staging = stg;
         ICP_CUDA_CHECK(cudaMemcpyAsync(stg, xyz, bytes, cudaMemcpyHostToDevice, st));
         raw = stg;
     }
     ICP_CUDA_CHECK(cudaMemcpyAsync(cs.counts, cs.h_counts, sizeof(uint32_t) * nseg, cudaMemcpyHostToDevice, st));
 
     const uint32_t ns = (uint32_t)nseg, mc = (uint32_t)max_count;
-    bbox_init_kernel<<<(ns * 8 + 255) / 256, 256, 0, st>>>(cs.bbox, ns, ctx->d_flags);
+    bbox_init_kernel<<<(ns * 8 + 255) / 256, 256, 0, st>>>(cs.bbox, ns, B.d_flags);
     {
         uint32_t bx = (uint32_t)((max_count + 256 * 8 - 1) / (256 * 8));
         uint32_t cap_bx = (uint32_t)((ctx->sm_count * 8 + ns - 1) / ns);
         if (bx > cap_bx) bx = cap_bx;
         if (bx < 1) bx = 1;
         dim3 grid(bx, ns);
-        bbox_kernel<<<grid, 256, 0, st>>>(raw, stride_bytes, cs.counts, mc, cs.bbox, ctx->d_flags);
+        bbox_kernel<<<grid, 256, 0, st>>>(raw, stride_bytes, cs.counts, mc, cs.bbox, B.d_flags);
     }
     bbox_finish_kernel<<<(ns + 127) / 128, 128, 0, st>>>(cs.bbox, cs.counts, cs.bb_lo, cs.bb_hi, ns);
     const uint32_t gb = (uint32_t)((slots + 255) / 256);
     curve_key_kernel<<<gb, 256, 0, st>>>(raw, stride_bytes, cs.counts, mc, sh.pitch, ns, cs.bb_lo, cs.bb_hi,
-                                      ctx->keys_a, ctx->vals_a);
+                                      B.keys_a, B.vals_a);
     int seg_bits = 0;
     while ((1ull << seg_bits) < nseg) seg_bits++;
     int end_bit = (nseg > 1) ? 32 + seg_bits : 31;
     size_t temp_bytes = 0;
-    ICP_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, ctx->keys_a, ctx->keys_b, ctx->vals_a,
-                                                   ctx->vals_b, slots, 0, end_bit, st));
+    ICP_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, B.keys_a, B.keys_b, B.vals_a,
+                                                   B.vals_b, slots, 0, end_bit, st));
     {
-        char* tmp = (char*)ctx->cub_temp;
-        if ((rc = icp_reserve(ctx, &tmp, &ctx->cub_temp_bytes, temp_bytes))) return rc;
-        ctx->cub_temp = tmp;
+        char* tmp = (char*)B.cub_temp;
+        if ((rc = icp_reserve(ctx, &tmp, &B.cub_temp_bytes, temp_bytes))) return rc;
+        B.cub_temp = tmp;
     }
-    ICP_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(ctx->cub_temp, temp_bytes, ctx->keys_a, ctx->keys_b, ctx->vals_a,
-                                                   ctx->vals_b, slots, 0, end_bit, st));
-    gather_kernel<<<gb, 256, 0, st>>>(raw, stride_bytes, cs.counts, mc, sh.pitch, ns, ctx->vals_b, cs.pts,
+    ICP_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(B.cub_temp, temp_bytes, B.keys_a, B.keys_b, B.vals_a,
+                                                   B.vals_b, slots, 0, end_bit, st));
+    gather_kernel<<<gb, 256, 0, st>>>(raw, stride_bytes, cs.counts, mc, sh.pitch, ns, B.vals_b, cs.pts,
                                       cs.pos_of_orig);
     {
         size_t nfl = nodes * 48;
@@ -344,10 +386,16 @@ int icp_build_cloudset(icpsymm_ctx* ctx, CloudSet& cs, const float* xyz, bool on
     }
     ICP_CUDA_CHECK(cudaMemsetAsync(cs.nrm, 0, slots * sizeof(float4), st));
     ICP_CUDA_CHECK(cudaGetLastError());
-    int h_flag = 0;
-    ICP_CUDA_CHECK(cudaMemcpyAsync(&h_flag, ctx->d_flags, sizeof(int), cudaMemcpyDeviceToHost, st));
-    ICP_CUDA_CHECK(cudaStreamSynchronize(st));
-    if (h_flag) return icp_fail_msg(ctx, ICPSYMM_ERR_NONFINITE, "cloud holds NaN/Inf coordinates");
+    ICP_CUDA_CHECK(cudaMemcpyAsync(B.h_flag, B.d_flags, sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (ctx->opt_async_setup && st != ctx->stream) {
+        // asynchronous setup: no host wait here; the flag is read at the next point that hands data
+        // to the host (icp_join_clouds), so the upload of the other cloud overlaps this build
+        icp_cloud_done(ctx, cs);
+        cs.pending_check = true;
+    } else {
+        ICP_CUDA_CHECK(cudaStreamSynchronize(st));
+        if (*B.h_flag) return icp_fail_msg(ctx, ICPSYMM_ERR_NONFINITE, "cloud holds NaN/Inf coordinates");
+    }
     cs.nseg = ns; cs.max_count = mc; cs.total = total; cs.shape = sh; cs.valid = true;
     return ICPSYMM_OK;
 }

@@ -24,6 +24,9 @@ struct CloudSet {
     uint32_t* h_counts = nullptr; // host copy
     size_t cap_pts = 0, cap_nodes = 0, cap_seg = 0;
     bool valid = false, has_normals = false;
+    int slot = 0;                 // 0 = source, 1 = target: selects the build scratch and the aux stream
+    bool on_aux = false;          // work of this cloud is outstanding on its aux stream (async setup)
+    bool pending_check = false;   // the non-finite flag of the last build has not been read yet
 
     CloudView view() const {
         CloudView v;
@@ -46,6 +49,17 @@ struct GraphKey {
     }
 };
 
+// scratch of one index build; one per cloud slot so that the two builds may overlap
+struct BuildScratch {
+    void* staging = nullptr;      size_t staging_bytes = 0;
+    unsigned long long *keys_a = nullptr, *keys_b = nullptr;
+    uint32_t *vals_a = nullptr, *vals_b = nullptr;
+    size_t sort_cap = 0;
+    void* cub_temp = nullptr;     size_t cub_temp_bytes = 0;
+    int* d_flags = nullptr;       // [0] non-finite count
+    int* h_flag = nullptr;        // pinned mirror
+};
+
 struct icpsymm_ctx {
     int device = 0;
     int sm_count = 148;
@@ -55,13 +69,11 @@ struct icpsymm_ctx {
 
     CloudSet src, tgt;
 
-    // build scratch (grow-only)
-    void* staging = nullptr;      size_t staging_bytes = 0;
-    unsigned long long *keys_a = nullptr, *keys_b = nullptr;
-    uint32_t *vals_a = nullptr, *vals_b = nullptr;
-    size_t sort_cap = 0;
-    void* cub_temp = nullptr;     size_t cub_temp_bytes = 0;
-    int* d_flags = nullptr;       // [0] non-finite count
+    // build scratch (grow-only) and the aux streams of the asynchronous setup
+    BuildScratch scratch[2];
+    cudaStream_t aux[2] = {nullptr, nullptr};
+    cudaEvent_t ready[2] = {nullptr, nullptr};
+    cudaEvent_t fork_ev = nullptr;
 
     // loop state
     SegState* d_state = nullptr;  size_t state_cap = 0;
@@ -85,6 +97,7 @@ struct icpsymm_ctx {
     int opt_warm_start = 1;
     int opt_trace = 0;
     int opt_grid_blocks = 0;
+    int opt_async_setup = 0;
 
     // graph cache
     cudaGraphExec_t graph_exec = nullptr;
@@ -111,6 +124,13 @@ template <typename T>
 int icp_reserve(icpsymm_ctx* ctx, T** p, size_t* cap, size_t need);   // grow-only cudaMalloc, element counts
 
 // index_build.cu
+// stream the work of cloud `cs` goes to: the context stream, or (ICPSYMM_OPT_ASYNC_SETUP) the
+// cloud's aux stream, forked from the context stream; icp_cloud_done marks the end of that work
+cudaStream_t icp_cloud_stream(icpsymm_ctx* ctx, CloudSet& cs);
+void icp_cloud_done(icpsymm_ctx* ctx, CloudSet& cs);
+// make the context stream wait for outstanding aux work; with `check` also resolve deferred
+// non-finite checks (blocks the host on the build)
+int icp_join_clouds(icpsymm_ctx* ctx, bool check);
 TreeShape icp_make_shape(uint32_t max_count);
 int icp_build_cloudset(icpsymm_ctx* ctx, CloudSet& cs, const float* xyz, bool on_device, const uint32_t* counts,
                        size_t nseg, size_t max_count, size_t stride_bytes);

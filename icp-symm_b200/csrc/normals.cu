@@ -171,12 +171,14 @@ int icp_estimate_normals(icpsymm_ctx* ctx, CloudSet& cs, int k, const float vp[3
     P.k = k;
     size_t slots = (size_t)cs.nseg * cs.shape.pitch;
     uint32_t grid = cs.nseg * ((cs.shape.pitch + 127u) / 128u);
-    ICP_CUDA_CHECK(cudaMemsetAsync(cs.nrm, 0, slots * sizeof(float4), ctx->stream));
-    if (k == 10) normals_kernel<10, true><<<grid, 128, 0, ctx->stream>>>(P);       // the reference's k (myicp.cpp:160)
-    else if (k < 10) normals_kernel<10, false><<<grid, 128, 0, ctx->stream>>>(P);
-    else if (k <= 16) normals_kernel<16, false><<<grid, 128, 0, ctx->stream>>>(P);
-    else normals_kernel<32, false><<<grid, 128, 0, ctx->stream>>>(P);
+    cudaStream_t st = icp_cloud_stream(ctx, cs);   // the cloud's aux stream under asynchronous setup
+    ICP_CUDA_CHECK(cudaMemsetAsync(cs.nrm, 0, slots * sizeof(float4), st));
+    if (k == 10) normals_kernel<10, true><<<grid, 128, 0, st>>>(P);       // the reference's k (myicp.cpp:160)
+    else if (k < 10) normals_kernel<10, false><<<grid, 128, 0, st>>>(P);
+    else if (k <= 16) normals_kernel<16, false><<<grid, 128, 0, st>>>(P);
+    else normals_kernel<32, false><<<grid, 128, 0, st>>>(P);
     ICP_CUDA_CHECK(cudaGetLastError());
+    icp_cloud_done(ctx, cs);
     cs.has_normals = true;
     return ICPSYMM_OK;
 }
@@ -189,6 +191,7 @@ static int ensure_io_n(icpsymm_ctx* ctx, size_t bytes) {
 }
 
 int icp_export_normals(icpsymm_ctx* ctx, const CloudSet& cs, float* out_host) {
+    { int jr = icp_join_clouds(ctx, true); if (jr < 0) return jr; }
     if (!cs.valid || !cs.has_normals) return icp_fail_msg(ctx, ICPSYMM_ERR_NOT_READY, "normals missing");
     size_t n = (size_t)cs.nseg * cs.max_count;
     int rc = ensure_io_n(ctx, n * sizeof(float4));
@@ -204,6 +207,7 @@ int icp_export_normals(icpsymm_ctx* ctx, const CloudSet& cs, float* out_host) {
 }
 
 int icp_import_normals(icpsymm_ctx* ctx, CloudSet& cs, const float* in_host) {
+    { int jr = icp_join_clouds(ctx, true); if (jr < 0) return jr; }
     if (!cs.valid) return icp_fail_msg(ctx, ICPSYMM_ERR_NOT_READY, "cloud not set");
     if (!in_host) return icp_fail_msg(ctx, ICPSYMM_ERR_INVALID, "null normals");
     size_t n = (size_t)cs.nseg * cs.max_count;

@@ -17,6 +17,8 @@ MyICP::MyICP(int device) : max_iters(10), diff_threshold(1.f) {
     result_.transform = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
     status_ = icpsymm_create(&ctx_, device);
     if (status_ != ICPSYMM_OK) ctx_ = nullptr;   // no CPU fallback: every later call reports the error
+    // upload, index build and normals of the two clouds run on their own streams and overlap
+    else icpsymm_set_option(ctx_, ICPSYMM_OPT_ASYNC_SETUP, 1.0);
 }
 
 MyICP::~MyICP() {

@@ -69,7 +69,11 @@ enum {
     ICPSYMM_OPT_KERNEL_TIMING = 5,  /* 1 = per-kernel CUDA-event timing (forces stream mode) */
     ICPSYMM_OPT_WARM_START = 6,     /* 1 (default) = seed each search with the previous correspondence */
     ICPSYMM_OPT_TRACE = 7,          /* 1 = keep per-search transform + diff (icpsymm_get_trace) */
-    ICPSYMM_OPT_GRID_BLOCKS = 8     /* blocks per pair for the search kernel, 0 = auto */
+    ICPSYMM_OPT_GRID_BLOCKS = 8,    /* blocks per pair for the search kernel, 0 = auto */
+    ICPSYMM_OPT_ASYNC_SETUP = 9     /* 1 = set_source / set_target / estimate_normals return without waiting: each cloud is
+                                       uploaded, indexed and given normals on its own stream, so the upload of one cloud
+                                       overlaps the build of the other; a NaN/Inf input is then reported by the next call
+                                       that returns data (register, find_correspondences, get_*, synchronize) */
 };
 
 /* ---- lifetime (MyICP::MyICP / ~MyICP, myicp.cpp:6-18) ---- */

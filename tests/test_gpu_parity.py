@@ -529,3 +529,32 @@ def test_normals_knn_ties_by_lowest_index(ctx):
     assert ok.mean() > 0.5
     assert _angle(dn[ok, :3], on[ok, :3]).max() < 1e-4
     assert np.allclose(dn[ok, 3], on[ok, 3], atol=2e-5)
+
+
+def test_async_setup_overlaps_without_changing_results(cat, cat_out):
+    """ICPSYMM_OPT_ASYNC_SETUP: per-cloud streams, no host waits in set_* / estimate_normals; same bits out,
+    and a NaN input is reported by the next call that returns data"""
+    a, b = icp.Context(0), icp.Context(0)
+    try:
+        b.set_option(icp.OPT_ASYNC_SETUP, 1)
+        for c in (a, b):
+            c.set_source(cat); c.set_target(cat_out); c.estimate_normals(10)
+        Ta, sa, _ = a.register_symm(50, 1.0)
+        Tb, sb, _ = b.register_symm(50, 1.0)
+        assert np.array_equal(Ta, Tb) and sa["diff"] == sb["diff"] and sa["iters"] == sb["iters"] == 5
+        assert np.array_equal(a.get_normals(1), b.get_normals(1))
+        for _ in range(3):                                    # re-upload while the previous result is still being read
+            b.set_source(cat); b.set_target(cat_out); b.estimate_normals(10)
+            Tc, sc, _ = b.register_symm(50, 1.0)
+            assert np.array_equal(Tc, Ta)
+        bad = cat_out.copy(); bad[11, 2] = np.inf
+        b.set_target(bad)                                     # returns at once: nothing has been checked yet
+        b.estimate_normals(10)
+        with pytest.raises(icp.IcpError) as e:
+            b.register_symm(5, 1.0)
+        assert e.value.status == icp.ERR_NONFINITE
+        b.set_target(cat_out); b.estimate_normals(10)         # the context recovers
+        Td, sd, _ = b.register_symm(50, 1.0)
+        assert np.array_equal(Td, Ta)
+    finally:
+        a.close(); b.close()
