@@ -124,6 +124,7 @@ int icpsymm_set_option(icpsymm_ctx* ctx, int key, double value) {
         case ICPSYMM_OPT_REL_DIFF_TOL: if (value < 0) return ICPSYMM_ERR_INVALID; ctx->opt_rel_diff_tol = value; break;
         case ICPSYMM_OPT_IDENTITY_PAIRS: ctx->opt_identity = value != 0; break;
         case ICPSYMM_OPT_MAX_PAIR_DIST: if (value < 0) return ICPSYMM_ERR_INVALID; ctx->opt_max_pair_dist = (float)value; break;
+        case ICPSYMM_OPT_MIN_NORMAL_DOT: ctx->opt_min_normal_dot = (value <= -1.0) ? -2.f : (float)value; break;
         case ICPSYMM_OPT_USE_GRAPH: ctx->opt_use_graph = (value == 2) ? 2 : (value != 0); break;
         case ICPSYMM_OPT_KERNEL_TIMING: ctx->opt_kernel_timing = value != 0; break;
         case ICPSYMM_OPT_WARM_START: ctx->opt_warm_start = value != 0; break;

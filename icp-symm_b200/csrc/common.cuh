@@ -79,6 +79,7 @@ struct LoopParams {
     float diff_threshold;
     double rel_diff_tol;
     float max_pair_d2;   // +inf = off
+    float min_normal_dot;  // -2 = off: reject pairs whose normals disagree (n_p . n_q below this)
     int identity_pairs;
     int warm_start;
     int trace;

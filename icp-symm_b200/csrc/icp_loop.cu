@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(kNNThreads, 4) nn_accum_kernel(const __grid_co
                 const float3 np = rotate_rn(sT, n0.x, n0.y, n0.z);
                 v[33] = __fsqrt_rn(bd2);
                 v[34] = bd2;
-                if (bd2 <= lp.max_pair_d2) {
+                if (bd2 <= lp.max_pair_d2 && (np.x * nq.x + np.y * nq.y + np.z * nq.z) >= lp.min_normal_dot) {
                     const float nx = np.x + nq.x, ny = np.y + nq.y, nz = np.z + nq.z;
                     const float ppx = p.x - sO[0], ppy = p.y - sO[1], ppz = p.z - sO[2];
                     const float qqx = q.x - sO[0], qqy = q.y - sO[1], qqz = q.z - sO[2];
@@ -647,6 +647,7 @@ int icp_run_loop(icpsymm_ctx* ctx, int max_iters, float thr, const float* T_init
     lp.diff_threshold = thr;
     lp.rel_diff_tol = ctx->opt_rel_diff_tol;
     lp.max_pair_d2 = ctx->opt_max_pair_dist > 0.f ? ctx->opt_max_pair_dist * ctx->opt_max_pair_dist : INFINITY;
+    lp.min_normal_dot = ctx->opt_min_normal_dot;
     lp.identity_pairs = ctx->opt_identity;
     lp.warm_start = ctx->opt_warm_start;
     lp.trace = ctx->opt_trace;

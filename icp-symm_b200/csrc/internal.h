@@ -92,6 +92,7 @@ struct icpsymm_ctx {
     double opt_rel_diff_tol = 0.0;
     int opt_identity = 0;
     float opt_max_pair_dist = 0.f;
+    float opt_min_normal_dot = -2.f;
     int opt_use_graph = 1;
     int opt_kernel_timing = 0;
     int opt_warm_start = 1;

@@ -70,6 +70,7 @@ enum {
     ICPSYMM_OPT_WARM_START = 6,     /* 1 (default) = seed each search with the previous correspondence */
     ICPSYMM_OPT_TRACE = 7,          /* 1 = keep per-search transform + diff (icpsymm_get_trace) */
     ICPSYMM_OPT_GRID_BLOCKS = 8,    /* blocks per pair for the search kernel, 0 = auto */
+    ICPSYMM_OPT_MIN_NORMAL_DOT = 10, /* <= -1 = off; reject pairs whose normals disagree: n_p . n_q < value */
     ICPSYMM_OPT_ASYNC_SETUP = 9     /* 1 = set_source / set_target / estimate_normals return without waiting: each cloud is
                                        uploaded, indexed and given normals on its own stream, so the upload of one cloud
                                        overlaps the build of the other; a NaN/Inf input is then reported by the next call

@@ -907,6 +907,11 @@ int orc_register_symm(const float* src, const float* src_n4, size_t ns, const fl
         float maxd2 = prm->max_pair_dist > 0 ? prm->max_pair_dist * prm->max_pair_dist : INFINITY;
         for (size_t i = 0; i < ns; i++) {
             if (d2[i] > maxd2) continue;
+            if (prm->min_normal_dot > -1.0f) {
+                const float* a = np + 4 * i;
+                const float* b = tgt_n4 + 4 * (size_t)idx[i];
+                if (a[0] * b[0] + a[1] * b[1] + a[2] * b[2] < prm->min_normal_dot) continue;
+            }
             memcpy(pk + 3 * m, p + 3 * i, 3 * sizeof(float));
             memcpy(npk + 4 * m, np + 4 * i, 4 * sizeof(float));
             memcpy(q + 3 * m, tgt + 3 * (size_t)idx[i], 3 * sizeof(float));

@@ -111,6 +111,7 @@ typedef struct {
     int threads;
     int use_brute;          /* 1 = brute-force NN instead of the kd-tree */
     float max_pair_dist;    /* 0 = off; else pairs with ||p-q|| > this are rejected (next-row f3) */
+    float min_normal_dot;   /* <= -1 = off; else pairs with n_p . n_q < this are rejected (next-row f3) */
 } orc_params;
 
 typedef struct {

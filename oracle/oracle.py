@@ -28,7 +28,7 @@ def build(force: bool = False) -> str:
 class Params(C.Structure):
     _fields_ = [("max_iters", C.c_int), ("diff_threshold", C.c_float), ("rel_diff_tol", C.c_double),
                 ("identity_pairs", C.c_int), ("threads", C.c_int), ("use_brute", C.c_int),
-                ("max_pair_dist", C.c_float)]
+                ("max_pair_dist", C.c_float), ("min_normal_dot", C.c_float)]
 
 
 class Stats(C.Structure):
@@ -237,11 +237,11 @@ def solve_compose(S, origin=(0, 0, 0)):
 
 
 def register_symm(src, src_n4, tgt, tgt_n4, max_iters=10, diff_threshold=1.0, rel_diff_tol=0.0,
-                  identity_pairs=False, threads=0, use_brute=False, max_pair_dist=0.0):
+                  identity_pairs=False, threads=0, use_brute=False, max_pair_dist=0.0, min_normal_dot=-2.0):
     """Oracle-C loop. Returns dict(T, stats, trace_T, trace_diff, idx)."""
     src, a = _f(src); src_n4, b = _f(src_n4); tgt, c = _f(tgt); tgt_n4, d = _f(tgt_n4)
     prm = Params(max_iters, diff_threshold, rel_diff_tol, int(identity_pairs), threads, int(use_brute),
-                 max_pair_dist)
+                 max_pair_dist, min_normal_dot)
     st = Stats()
     T = np.empty(16, np.float32)
     trT = np.zeros((max_iters + 1, 16), np.float32)

@@ -310,6 +310,15 @@ def test_max_pair_distance_rejection(ctx, cat, cat_out):
     r = orc.register_symm(cat, ns, cat_out, nt, max_iters=3, diff_threshold=1.0, max_pair_dist=25.0)
     assert st["iters"] == r["iters"] and st["pairs"] == r["pairs"]
     assert wl.rotation_angle(T, r["T"]) <= 1e-4 and np.allclose(T[:3, 3], r["T"][:3, 3], atol=1e-3)
+    # normal-compatibility rejection (the other half of SURVEY 8f row 3)
+    ctx.set_option(icp.OPT_MIN_NORMAL_DOT, 0.5)
+    try:
+        T, st, _ = ctx.register_symm(2, 1.0)
+    finally:
+        ctx.set_option(icp.OPT_MIN_NORMAL_DOT, -2.0)
+    r = orc.register_symm(cat, ns, cat_out, nt, max_iters=2, diff_threshold=1.0, min_normal_dot=0.5)
+    assert st["iters"] == r["iters"] and 0 < st["pairs"] < len(cat) and abs(int(st["pairs"]) - int(r["pairs"])) <= 2
+    assert wl.rotation_angle(T, r["T"]) <= 1e-3
 
 
 def test_batch_equals_single_pairs(ctx):
