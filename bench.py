@@ -94,6 +94,14 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
+def host_threads():
+    """all host threads this process may use (torchrun exports OMP_NUM_THREADS=1, which is not the machine)"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
 def make_pair(n, rank):
     src, tgt, T = wl.config_synth(n, seed=1234 + rank)
     return src, tgt, T
@@ -108,7 +116,7 @@ def run_reference(args, rank, world):
     src, tgt, _ = make_pair(n, 0)
     sample = min(n, args.cpu_sample or n)
     sel = np.sort(np.random.default_rng(7).choice(n, sample, replace=False)) if sample < n else np.arange(n)
-    threads = orc.num_threads()
+    threads = host_threads()
     times, iters = [], 0
     for s in range(args.warmup + args.steps):
         t0 = time.perf_counter()
@@ -312,7 +320,7 @@ def cpu_baseline(args, src, tgt, ctx):
     sample = min(n, args.cpu_sample or n)
     sel = np.sort(np.random.default_rng(7).choice(n, sample, replace=False))
     ns, nt = ctx.get_normals(0)[sel], ctx.get_normals(1)
-    threads = orc.num_threads()
+    threads = host_threads()
     t0 = time.perf_counter()
     r = orc.register_symm(src[sel], ns, tgt, nt, max_iters=MAX_ITERS, diff_threshold=DIFF_THR * sample / n,
                           rel_diff_tol=REL_TOL, threads=threads)
