@@ -163,15 +163,6 @@ __device__ __forceinline__ void box_bounds2(float lx0, float lx1, float ly0, flo
     b1 = __float_as_uint(__fadd_rn(__fadd_rn(sx1, sy1), sz1));
 }
 
-// lower bound of dist2_rn from (qx,qy,qz) to any point inside the box.  Same operation order as
-// dist2_rn: every step is monotone under round-to-nearest, so bound <= member distance exactly.
-__device__ __forceinline__ float box_dist2_rn(const float4& lo, const float4& hi, float qx, float qy, float qz) {
-    float ex = fmaxf(fmaxf(__fsub_rn(lo.x, qx), __fsub_rn(qx, hi.x)), 0.f);
-    float ey = fmaxf(fmaxf(__fsub_rn(lo.y, qy), __fsub_rn(qy, hi.y)), 0.f);
-    float ez = fmaxf(fmaxf(__fsub_rn(lo.z, qz), __fsub_rn(qz, hi.z)), 0.f);
-    return __fadd_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)), __fmul_rn(ez, ez));
-}
-
 // x' = (((T0*x)+(T1*y))+(T2*z))+T3, no FMA.  T is 3x4 row-major.
 __device__ __forceinline__ float3 apply_rn(const float* __restrict__ T, float x, float y, float z) {
     float3 r;

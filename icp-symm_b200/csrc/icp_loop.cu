@@ -57,7 +57,6 @@ struct SolveParams {
     const LoopParams* lp;
     const double* partial;
     double* gsum;
-    const uint32_t* src_counts;
     float* trace_T;
     double* trace_diff;
     uint32_t blocks_per_seg;
@@ -619,7 +618,6 @@ int icp_run_loop(icpsymm_ctx* ctx, int max_iters, float thr, const float* T_init
     uint32_t max_q = S.max_count;
     if (ctx->shard_world > 1) max_q = (uint32_t)((S.max_count + ctx->shard_world - 1) / ctx->shard_world) + 1;
     const uint32_t bps = choose_blocks_per_seg(ctx, nseg, max_q);
-    ctx->last_blocks_per_seg = bps;
 
     if ((rc = icp_reserve(ctx, &ctx->d_state, &ctx->state_cap, nseg))) return rc;
     if (ctx->h_state_cap < nseg) {
@@ -672,7 +670,7 @@ int icp_run_loop(icpsymm_ctx* ctx, int max_iters, float thr, const float* T_init
     np.blocks_per_seg = bps; np.shard_rank = ctx->shard_rank; np.shard_world = ctx->shard_world;
     SolveParams sp;
     sp.state = ctx->d_state; sp.lp = ctx->d_lp; sp.partial = ctx->partial; sp.gsum = ctx->gsum;
-    sp.src_counts = S.counts; sp.trace_T = ctx->opt_trace ? ctx->trace_T : nullptr;
+    sp.trace_T = ctx->opt_trace ? ctx->trace_T : nullptr;
     sp.trace_diff = ctx->opt_trace ? ctx->trace_diff : nullptr;
     sp.blocks_per_seg = bps; sp.trace_stride = ctx->trace_stride; sp.mode = single_search ? 3 : 0;
     if (!ctx->d_ctrl) {
@@ -708,7 +706,7 @@ int icp_run_loop(icpsymm_ctx* ctx, int max_iters, float thr, const float* T_init
         key.p0 = S.pts; key.p1 = T.pts; key.p2 = ctx->partial; key.p3 = ctx->corr_pos; key.p4 = ctx->d_state;
         key.p5 = ctx->opt_trace ? (const void*)ctx->trace_T : (const void*)T.nodes;
         key.shard_rank = ctx->shard_rank; key.shard_world = ctx->shard_world; key.trace = ctx->opt_trace;
-        key.comm_mode = ctx->opt_use_graph + 16 * ctx->peer_world;
+        key.mode = ctx->opt_use_graph + 16 * ctx->peer_world;
         // pointers of the remaining arrays change only together with the ones above (same reserve calls)
         if (!ctx->graph_exec || !(ctx->graph_key == key)) {
             if (ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }

@@ -40,11 +40,11 @@ struct GraphKey {
     int max_iters = -1;
     uint32_t nseg = 0, blocks_per_seg = 0, src_pitch = 0, tgt_pitch = 0;
     const void *p0 = nullptr, *p1 = nullptr, *p2 = nullptr, *p3 = nullptr, *p4 = nullptr, *p5 = nullptr;
-    int comm_mode = 0, shard_rank = 0, shard_world = 1, trace = 0;
+    int mode = 0, shard_rank = 0, shard_world = 1, trace = 0;   // mode: graph flavour + peer world
     bool operator==(const GraphKey& o) const {
         return max_iters == o.max_iters && nseg == o.nseg && blocks_per_seg == o.blocks_per_seg &&
                src_pitch == o.src_pitch && tgt_pitch == o.tgt_pitch && p0 == o.p0 && p1 == o.p1 && p2 == o.p2 &&
-               p3 == o.p3 && p4 == o.p4 && p5 == o.p5 && comm_mode == o.comm_mode && shard_rank == o.shard_rank &&
+               p3 == o.p3 && p4 == o.p4 && p5 == o.p5 && mode == o.mode && shard_rank == o.shard_rank &&
                shard_world == o.shard_world && trace == o.trace;
     }
 };
@@ -85,7 +85,6 @@ struct icpsymm_ctx {
     double* gsum = nullptr;       size_t gsum_cap = 0;
     float* trace_T = nullptr;     double* trace_diff = nullptr; size_t trace_cap = 0; int trace_stride = 0;
     void* io_buf = nullptr;       size_t io_bytes = 0;   // device scratch for exports/imports
-    uint32_t last_blocks_per_seg = 0;
     bool have_corr = false;
 
     // options
@@ -111,7 +110,6 @@ struct icpsymm_ctx {
     // multi-GPU
     int shard_rank = 0, shard_world = 1;
     void* nccl_comm = nullptr;
-    void* nccl_lib = nullptr;
     // NVLink peer exchange (comm.cu): my buffer + the mapped buffers of all ranks
     void* peer_local = nullptr;
     void* peer_ptrs[ICP_MAX_PEERS] = {nullptr};
