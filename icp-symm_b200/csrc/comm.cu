@@ -134,6 +134,8 @@ extern "C" int icpsymm_peer_attach(icpsymm_ctx* ctx, const void* handles, int n_
     ctx->peer_world = n_ranks;
     ctx->shard_rank = rank;
     ctx->shard_world = n_ranks;
+    // the captured loop graph holds the old peer pointers
+    if (ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }
     return ICPSYMM_OK;
 }
 
@@ -148,6 +150,7 @@ extern "C" int icpsymm_peer_detach(icpsymm_ctx* ctx) {
     if (ctx->peer_local) { cudaFree(ctx->peer_local); ctx->peer_local = nullptr; }
     if (ctx->peer_world > 1) { ctx->shard_rank = 0; ctx->shard_world = 1; }
     ctx->peer_world = 0;
+    if (ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }
     cudaGetLastError();
     return ICPSYMM_OK;
 }
