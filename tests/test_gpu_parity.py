@@ -249,6 +249,13 @@ def test_register_stream_mode_equals_graph_mode(ctx, cat, cat_out):
         ctx.set_option(icp.OPT_KERNEL_TIMING, 0)
     assert np.array_equal(Tg, Ts) and sg["iters"] == ss["iters"] and sg["diff"] == ss["diff"]
     assert ss["search_launches"] == ss["searches"] and ss["search_ms"] > 0
+    # the unrolled graph ((max_iters+1) x [search, solve] with early exits) is a third way to run the same loop
+    ctx.set_option(icp.OPT_USE_GRAPH, 2)
+    try:
+        Tu, su, _ = ctx.register_symm(50, 1.0)
+    finally:
+        ctx.set_option(icp.OPT_USE_GRAPH, 1)
+    assert np.array_equal(Tg, Tu) and su["iters"] == sg["iters"] and su["diff"] == sg["diff"]
     # warm start off must not change any result
     ctx.set_option(icp.OPT_WARM_START, 0)
     try:
