@@ -39,7 +39,7 @@ __device__ __forceinline__ void jacobi_rotate(float& app, float& aqq, float& apq
 }
 
 template <int KMAX, bool EXACT>
-__global__ void __launch_bounds__(128) normals_kernel(const __grid_constant__ NormalParams P) {
+__global__ void __launch_bounds__(128, (KMAX <= 16) ? 7 : 4) normals_kernel(const __grid_constant__ NormalParams P) {
     // one block = 128 consecutive sorted points of ONE segment, so that a warp never straddles two
     // clouds and its 32 lanes can walk the hierarchy together
     const uint32_t pitch = P.cloud.shape.pitch;
@@ -50,13 +50,13 @@ __global__ void __launch_bounds__(128) normals_kernel(const __grid_constant__ No
     const bool active = i < cnt;
     const float4* __restrict__ pts = P.cloud.pts + (size_t)seg * pitch;
     const WideNode* __restrict__ boxes = P.cloud.nodes + (size_t)seg * P.cloud.shape.nodes_per_seg;
-    const uint32_t* __restrict__ pos_of_orig = P.cloud.pos_of_orig + (size_t)seg * pitch;
     const float4 q = active ? ldg4(pts + i) : make_float4(0.f, 0.f, 0.f, 0.f);
     const int k = P.k;
 
     // first bound: the query's own leaf group and its neighbours along the curve
-    __shared__ unsigned long long s_park[ICP_KNN_BUF][128];   // [slot][thread]: conflict-free columns
-    KList<KMAX, EXACT> L;
+    typedef KList<KMAX, EXACT> List;
+    __shared__ unsigned long long s_park[List::CAP][128];   // [slot][thread]: conflict-free columns
+    List L;
     L.init(&s_park[0][threadIdx.x], 128);
     const uint32_t n_groups = pitch / ICP_LEAF;
     const uint32_t g = active ? i / ICP_LEAF : 0u, w = (k <= 16) ? 1u : 2u;
@@ -68,28 +68,23 @@ __global__ void __launch_bounds__(128) normals_kernel(const __grid_constant__ No
         if (w_lo != 0xffffffffu) {
 #pragma unroll 1
             for (uint32_t gg = w_lo; gg <= w_hi; gg++) {
-                const bool mine = active && gg >= g_lo && gg <= g_hi;
-                const unsigned long long saved = L.kth;
-                if (!mine) L.kth = 0ull;
-                knn_offer_leaf(L, k, pts + (size_t)gg * ICP_LEAF, q.x, q.y, q.z);
-                if (!mine) L.kth = saved;
-                L.maybe_flush(k);
+                knn_offer_leaf(L, pts, gg, q.x, q.y, q.z, active && gg >= g_lo && gg <= g_hi);
+                L.maybe_flush(k, pts);
             }
         }
     }
     knn_traverse_warp<KMAX, EXACT>(P.cloud.shape, boxes, pts, q.x, q.y, q.z, k, g_lo, g_hi, active, L);
     if (!active) return;
 
-    // covariance of the neighbourhood, coordinates relative to the query point
+    // covariance of the neighbourhood (the parked k nearest), coordinates relative to the query point
     float ux[KMAX], uy[KMAX], uz[KMAX];
     int m = 0;
     float mx = 0.f, my = 0.f, mz = 0.f;
 #pragma unroll
     for (int t = 0; t < KMAX; t++) {
         ux[t] = uy[t] = uz[t] = 0.f;
-        if (t < k && L.key[t] != ~0ull) {
-            uint32_t id = (uint32_t)(L.key[t] & 0xffffffffull);
-            float4 c = ldg4(pts + pos_of_orig[id]);
+        if (t < L.cnt) {
+            const float4 c = ldg4(pts + (uint32_t)L.buf[t * L.stride]);
             ux[t] = c.x - q.x; uy[t] = c.y - q.y; uz[t] = c.z - q.z;
             mx += ux[t]; my += uy[t]; mz += uz[t];
             m++;
@@ -102,7 +97,7 @@ __global__ void __launch_bounds__(128) normals_kernel(const __grid_constant__ No
         float cxx = 0.f, cxy = 0.f, cxz = 0.f, cyy = 0.f, cyz = 0.f, czz = 0.f;
 #pragma unroll
         for (int t = 0; t < KMAX; t++) {
-            if (t < k && L.key[t] != ~0ull) {
+            if (t < m) {
                 float ex = ux[t] - mx, ey = uy[t] - my, ez = uz[t] - mz;
                 cxx += ex * ex; cxy += ex * ey; cxz += ex * ez; cyy += ey * ey; cyz += ey * ez; czz += ez * ez;
             }

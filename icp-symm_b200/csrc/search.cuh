@@ -19,7 +19,6 @@
 #include "common.cuh"
 
 #define ICP_INF_BITS 0x7f800000u
-#define ICP_KNN_BUF 32                   // parked kNN candidates per lane (shared memory, 8 B each)
 
 // best candidate so far as ONE 64-bit key, (d2 bits << 32) | original index: d2 >= 0, so unsigned
 // integer order on the key is exactly the (d2, lowest original index) order the oracle defines, and
@@ -244,98 +243,121 @@ __device__ __forceinline__ void nn_traverse_warp(const TreeShape& sh, const Wide
     wide_traverse_warp(sh, seg_nodes, qx, qy, qz, active, v);
 }
 
-// ---- k nearest: ascending list of keys (d2 bits << 32 | original index), k <= KMAX at run time ----
-// d2 >= 0 or +inf, so its bit pattern orders like an unsigned integer; an unfilled slot is ~0.
-// EXACT = the list is used with k == KMAX (the reference's k = 10, myicp.cpp:160): no per-slot
-// `j < k` predicate and the k-th best is simply the last slot.
+// ---- k nearest ------------------------------------------------------------------------------
+// Per lane: (1) the ascending bit patterns of the k smallest squared distances seen so far, in
+// registers -- only the VALUES, so that merging a candidate is a branch-free min/max chain (two
+// instructions per slot, nothing to carry along); (2) the candidates themselves, parked in a
+// per-lane shared-memory column as (d2 bits << 32 | sorted position) whenever they do not exceed
+// the current k-th distance.  d2 >= 0, so its bit pattern orders like an unsigned integer.
+//   flush    merges the distances of the newly parked candidates into the register list (all lanes
+//            run the chain together, max-over-lanes(count) rounds);
+//   compact  drops the parked candidates that the tightened k-th distance has overtaken; if more than
+//            k remain (several candidates share the k-th distance) the largest (d2, original index)
+//            is removed until k are left -- the oracle's tie rule, lowest original index first.
+// After a final flush + compact the column holds exactly the k nearest neighbours.
+// EXACT = the list is used with k == KMAX (the reference's k = 10, myicp.cpp:160).
+#define ICP_KNN_UNFILLED 0xfffffffeu     // above every distance, below the 0xffffffff of padding points
 template <int KMAX, bool EXACT>
 struct KList {
-    unsigned long long key[KMAX];
-    unsigned long long kth;  // key[k-1]: the current k-th best
-    // candidates that beat kth are first parked in a per-lane shared-memory column and merged into
-    // the list in bursts (flush): the long insertion body then runs max-over-lanes(count) times per
-    // burst with most lanes busy, instead of once per candidate with one or two lanes busy
+    static constexpr int CAP = (KMAX <= 16) ? 32 : 48;   // parked candidates per lane (8 B each)
+    uint32_t d[KMAX];
+    uint32_t kth;              // d[k-1]: the current k-th smallest squared distance (bits)
     unsigned long long* buf;   // this lane's column: buf[slot * stride]
-    int stride, cnt;
+    int stride, cnt, done;     // cnt parked, the first `done` of them already merged into d[]
 
     __device__ __forceinline__ void init(unsigned long long* column, int column_stride) {
 #pragma unroll
-        for (int j = 0; j < KMAX; j++) key[j] = ~0ull;
-        kth = ~0ull;
-        buf = column; stride = column_stride; cnt = 0;
+        for (int j = 0; j < KMAX; j++) d[j] = ICP_KNN_UNFILLED;
+        kth = ICP_KNN_UNFILLED;
+        buf = column; stride = column_stride; cnt = 0; done = 0;
     }
-    __device__ __forceinline__ void flush(int k) {
-        const int rounds = __reduce_max_sync(0xffffffffu, cnt);
-#pragma unroll 1
-        for (int r = 0; r < rounds; r++) {
-            const unsigned long long cand = (r < cnt) ? buf[r * stride] : ~0ull;
-            if (cand < kth) insert(k, cand);
-        }
-        cnt = 0;
-    }
-    // merge when some lane has no room left for another leaf group
-    __device__ __forceinline__ void maybe_flush(int k) {
-        if (__any_sync(0xffffffffu, cnt > ICP_KNN_BUF - ICP_LEAF)) flush(k);
-    }
-    // sorted insert of a key that is known to be < kth: slot j keeps its key while it is smaller
-    // than the new one, otherwise it takes the new key (first such slot) or its left neighbour
-    __device__ __forceinline__ void insert(int k, unsigned long long kk) {
-        bool prev_less = true;   // "key[j-1] < kk" for j = 0
-        unsigned long long prev_key = 0ull;
+    // sorted insert of one value: slot j keeps min(d[j], max(d[j-1], v))
+    __device__ __forceinline__ void insert(int k, uint32_t v) {
+        uint32_t prev = 0u;
 #pragma unroll
         for (int j = 0; j < KMAX; j++) {
-            const unsigned long long cur = key[j];
-            const bool less = cur < kk;
-            if (EXACT || j < k) key[j] = less ? cur : (prev_less ? kk : prev_key);
-            prev_less = less;
-            prev_key = cur;
+            const uint32_t cur = d[j];
+            d[j] = min(cur, max(prev, v));
+            prev = cur;
         }
         if (EXACT) {
-            kth = key[KMAX - 1];
+            kth = d[KMAX - 1];
         } else {
-            // k-th best = max of the first k slots (written as a max so the compiler keeps key[] in
-            // registers instead of turning a select chain into a dynamic local-memory index)
-            unsigned long long t = 0ull;
+            // d[k-1] as a max over the first k slots (a select chain would become a dynamic local-memory index)
+            uint32_t t = 0u;
 #pragma unroll
-            for (int j = 0; j < KMAX; j++) {
-                unsigned long long c = (j < k) ? key[j] : 0ull;
-                t = c > t ? c : t;
-            }
+            for (int j = 0; j < KMAX; j++) t = max(t, (j < k) ? d[j] : 0u);
             kth = t;
         }
     }
-    __device__ __forceinline__ void offer(int k, float d2, uint32_t id) {
-        const unsigned long long kk = ((unsigned long long)__float_as_uint(d2) << 32) | id;
-        if (kk < kth) insert(k, kk);
+    __device__ __forceinline__ void flush(int k) {
+        const int rounds = __reduce_max_sync(0xffffffffu, cnt - done);
+        const uint32_t* hi = reinterpret_cast<const uint32_t*>(buf) + 1;   // high words: the distances
+#pragma unroll 2
+        for (int r = 0; r < rounds; r++) {
+            const int idx = done + r;
+            insert(k, idx < cnt ? hi[2 * idx * stride] : 0xffffffffu);
+        }
+        done = cnt;
     }
-    __device__ __forceinline__ uint32_t bound_bits() const { return (uint32_t)(kth >> 32); }
+    __device__ __forceinline__ void compact(int k, const float4* __restrict__ pts) {
+        const int n = __reduce_max_sync(0xffffffffu, cnt);
+        int w = 0;
+#pragma unroll 4
+        for (int r = 0; r < n; r++) {
+            if (r < cnt) {
+                const unsigned long long e = buf[r * stride];
+                if ((uint32_t)(e >> 32) <= kth) { buf[w * stride] = e; w++; }
+            }
+        }
+        // surplus ties at the k-th distance (rare): drop the largest original index until k remain
+        while (w > k) {
+            int worst = 0;
+            unsigned long long worst_key = 0ull;
+            for (int r = 0; r < w; r++) {
+                const unsigned long long e = buf[r * stride];
+                const unsigned long long key = (e & 0xffffffff00000000ull) | __float_as_uint(ldg4(pts + (uint32_t)e).w);
+                if (key >= worst_key) { worst_key = key; worst = r; }
+            }
+            w--;
+            buf[worst * stride] = buf[w * stride];
+        }
+        cnt = done = w;
+    }
+    // merge and prune when some lane has no room left for another leaf group
+    __device__ __forceinline__ void maybe_flush(int k, const float4* __restrict__ pts) {
+        if (__any_sync(0xffffffffu, cnt > CAP - ICP_LEAF)) { flush(k); compact(k, pts); }
+    }
+    __device__ __forceinline__ uint32_t bound_bits() const { return kth; }
 };
 
-// offer the 8 points of one leaf group: form the 8 keys and park the ones that beat the lane's current
-// k-th best; the caller merges (maybe_flush) when a lane's column is nearly full.  Until the merge the pruning bound is the
-// (slightly stale, hence only looser) k-th best of the last merge: exactness is unaffected.
+// offer the 8 points of leaf group g: park the ones that do not exceed the lane's current k-th distance
+// (`take` = false makes the lane a bystander).  Until the next flush the pruning bound is the slightly
+// stale, hence only looser, k-th distance of the last merge: exactness is unaffected.
 template <int KMAX, bool EXACT>
-__device__ __forceinline__ void knn_offer_leaf(KList<KMAX, EXACT>& L, int k, const float4* __restrict__ lp,
-                                               float qx, float qy, float qz) {
-    unsigned long long kk[ICP_LEAF];
+__device__ __forceinline__ void knn_offer_leaf(KList<KMAX, EXACT>& L, const float4* __restrict__ pts, uint32_t g,
+                                               float qx, float qy, float qz, bool take) {
+    uint32_t db[ICP_LEAF];
+    const float4* lp = pts + (size_t)g * ICP_LEAF;
     const NegQuery nq = make_neg_query(qx, qy, qz);
 #pragma unroll
     for (int j = 0; j < ICP_LEAF; j++) {
         const float4 c = ldg4(lp + j);
-        const uint32_t id = __float_as_uint(c.w);
-        const float d = dist2_packed(nq, c);
-        kk[j] = (id != (uint32_t)ICP_INVALID_ID) ? (((unsigned long long)__float_as_uint(d) << 32) | id) : ~0ull;
+        const float dd = dist2_packed(nq, c);
+        db[j] = (__float_as_uint(c.w) != (uint32_t)ICP_INVALID_ID) ? __float_as_uint(dd) : 0xffffffffu;
     }
-    // park the candidates that beat the current k-th best (warp-uniform call: every lane runs this)
+    const uint32_t thr = take ? L.kth : 0u;
 #pragma unroll
     for (int j = 0; j < ICP_LEAF; j++) {
-        if (kk[j] < L.kth) { L.buf[L.cnt * L.stride] = kk[j]; L.cnt++; }
+        if (db[j] <= thr && take) {
+            L.buf[L.cnt * L.stride] = ((unsigned long long)db[j] << 32) | (g * ICP_LEAF + (uint32_t)j);
+            L.cnt++;
+        }
     }
 }
 
 // Leaves [g_lo, g_hi] were already offered by the caller (the query's own neighbourhood along the
-// curve, which gives a finite first bound) and are skipped so that no candidate enters the list
-// twice.  Sentinel padding points are ignored.
+// curve, which gives a finite first bound) and are skipped so that no candidate is parked twice.
 template <int KMAX, bool EXACT>
 struct KnnVisitor {
     KList<KMAX, EXACT>& L;
@@ -346,16 +368,13 @@ struct KnnVisitor {
     bool active;
     __device__ __forceinline__ uint32_t bound_bits() const { return L.bound_bits(); }
     __device__ __forceinline__ void leaf(uint32_t g) {
-        // warp-uniform call; a lane skips the leaves it has already seen by making its keys inert
-        const bool skip = !active || (g >= g_lo && g <= g_hi);
-        const unsigned long long saved = L.kth;
-        if (skip) L.kth = 0ull;                 // nothing beats 0: no insertion for this lane
-        knn_offer_leaf(L, k, pts + (size_t)g * ICP_LEAF, qx, qy, qz);
-        if (skip) L.kth = saved;
-        L.maybe_flush(k);
+        // warp-uniform call; a lane sits out the leaves it has already seen
+        knn_offer_leaf(L, pts, g, qx, qy, qz, active && !(g >= g_lo && g <= g_hi));
+        L.maybe_flush(k, pts);
     }
 };
 
+// on return every lane's column holds exactly its k nearest neighbours (L.cnt of them)
 template <int KMAX, bool EXACT>
 __device__ __forceinline__ void knn_traverse_warp(const TreeShape& sh, const WideNode* __restrict__ seg_nodes,
                                                   const float4* __restrict__ seg_pts, float qx, float qy, float qz,
@@ -365,4 +384,5 @@ __device__ __forceinline__ void knn_traverse_warp(const TreeShape& sh, const Wid
     L.flush(k);                                   // the caller's window scan
     wide_traverse_warp(sh, seg_nodes, qx, qy, qz, active, v);
     L.flush(k);
+    L.compact(k, seg_pts);
 }
