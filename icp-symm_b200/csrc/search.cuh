@@ -19,6 +19,12 @@
 #include "common.cuh"
 
 #define ICP_INF_BITS 0x7f800000u
+#ifndef ICP_FAR_FACTOR
+#define ICP_FAR_FACTOR 4.f               // far mode while the largest bound^2 exceeds this times the squared patch diagonal
+#endif
+#ifndef ICP_DENSE_MIN
+#define ICP_DENSE_MIN 4                  // stage-1 survivors from which the all-children exact test is cheaper than per-child shuffles
+#endif
 
 // best candidate so far as ONE 64-bit key, (d2 bits << 32) | original index: d2 >= 0, so unsigned
 // integer order on the key is exactly the (d2, lowest original index) order the oracle defines, and
@@ -145,7 +151,7 @@ __device__ __forceinline__ uint32_t warp_node_test(const WideNode* __restrict__ 
     pref = (int)(kmin1 & 7u);
     // stage 2: exact, per lane, only for the survivors
     uint32_t mask2 = 0;
-    if (__popc(mask1) > 3) {
+    if (__popc(mask1) >= ICP_DENSE_MIN) {
         uint32_t kmin;
         const uint32_t mine = dense_children_test(nd, qx, qy, qz, my_bound, kmin);
         mask2 = __reduce_or_sync(0xffffffffu, active ? mine : 0u) & mask1;
@@ -184,7 +190,7 @@ __device__ __forceinline__ void wide_traverse_warp(const TreeShape& sh, const Wi
     uint32_t max_bound = __reduce_max_sync(0xffffffffu, active ? v.bound_bits() : 0u);
     // far mode while the largest bound exceeds 4x the squared patch diagonal (both warp-uniform)
     const float pdx = pb.hix - pb.lox, pdy = pb.hiy - pb.loy, pdz = pb.hiz - pb.loz;
-    const uint32_t far_thr = __float_as_uint(4.f * (pdx * pdx + pdy * pdy + pdz * pdz));
+    const uint32_t far_thr = __float_as_uint(ICP_FAR_FACTOR * (pdx * pdx + pdy * pdy + pdz * pdz));
     bool far_mode = max_bound > far_thr;
     uint32_t stale = 0;   // bit l: the pending mask of level l predates the latest bound improvement
     int l = top, pref;
