@@ -147,9 +147,9 @@ __global__ void __launch_bounds__(kNNThreads, 4) nn_accum_kernel(const __grid_co
         }
         // warp-synchronous exact search: the 32 lanes are 32 neighbouring source points
         if (!lp.identity_pairs && nt > 0) nn_traverse_warp(P.tgt.shape, tbox, tpts, p.x, p.y, p.z, active, b);
-        float v[ICP_NSUMS];   // declared after the walk so that none of it is live across it
+        float v[40];   // declared after the walk so that none of it is live across it; ICP_NSUMS = 37 used
 #pragma unroll
-        for (int k = 0; k < ICP_NSUMS; k++) v[k] = 0.f;
+        for (int k = 0; k < 40; k++) v[k] = 0.f;
         if (active) {
             // the key carries the original index; the sorted position comes from the inverse permutation
             const uint32_t bpos = (b.id() != (uint32_t)ICP_INVALID_ID)
@@ -186,16 +186,35 @@ __global__ void __launch_bounds__(kNNThreads, 4) nn_accum_kernel(const __grid_co
                 }
             }
         }
+        // transposing warp reduction: after the steps 16, 8, 4, 2, 1 lane L holds the warp total of
+        // v[L] (31 shuffles for 32 values instead of 160): a lane keeps the half of the values whose
+        // index bit matches its own lane bit and hands the other half to its partner
 #pragma unroll
-        for (int k = 0; k < ICP_NSUMS; k++) {
-            float x = v[k];
-            x += __shfl_xor_sync(0xffffffffu, x, 16);
-            x += __shfl_xor_sync(0xffffffffu, x, 8);
-            x += __shfl_xor_sync(0xffffffffu, x, 4);
-            x += __shfl_xor_sync(0xffffffffu, x, 2);
-            x += __shfl_xor_sync(0xffffffffu, x, 1);
-            if (lane == 0) wacc[warp][k] += (double)x;
+        for (int off = 16; off >= 1; off >>= 1) {
+            const bool hi = (lane & off) != 0;
+#pragma unroll
+            for (int j = 0; j < off; j++) {
+                const float keep = hi ? v[j + off] : v[j];
+                const float send = hi ? v[j] : v[j + off];
+                v[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+            }
         }
+        // slots 32..39 (five used): transpose over lane bits 4, 3, 2, then a butterfly over bits 1, 0
+#pragma unroll
+        for (int off = 16, n = 4; n >= 1; off >>= 1, n >>= 1) {
+            const bool hi = (lane & off) != 0;
+#pragma unroll
+            for (int j = 0; j < n; j++) {
+                const float keep = hi ? v[32 + j + n] : v[32 + j];
+                const float send = hi ? v[32 + j] : v[32 + j + n];
+                v[32 + j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+            }
+        }
+        v[32] += __shfl_xor_sync(0xffffffffu, v[32], 2);
+        v[32] += __shfl_xor_sync(0xffffffffu, v[32], 1);
+        // every lane adds its own total (fp64, this warp's accumulator row)
+        wacc[warp][lane] += (double)v[0];
+        if ((lane & 3) == 0 && 32 + (lane >> 2) < ICP_NSUMS) wacc[warp][32 + (lane >> 2)] += (double)v[32];
     }
     __syncthreads();
     if (tid < ICP_NSUMS) {
@@ -571,7 +590,13 @@ static uint32_t choose_blocks_per_seg(const icpsymm_ctx* ctx, uint32_t nseg, uin
     uint32_t bps;
     if (ctx->opt_grid_blocks > 0) bps = (uint32_t)ctx->opt_grid_blocks;
     else {
-        uint32_t target = (uint32_t)ctx->sm_count * 16u;   // 4 resident blocks/SM x 4 waves: measured best at 1M
+        const uint32_t resident = (uint32_t)ctx->sm_count * 4u;   // 4 blocks per SM
+        uint32_t target = resident * 4u;                          // 4 waves: measured best at 1M and beyond
+        // between one and two tiles per block the blocks with two tiles (lowest indices) start first and
+        // the one-tile blocks fill the tail; about 3/4 of the tile count, rounded to whole waves, balances
+        // best (1M points: 3907 tiles -> 2960 blocks, 5 % faster than 2368)
+        if (nseg == 1 && ntiles > target && ntiles < 2u * target)
+            target = ((ntiles * 3u / 4u + resident - 1u) / resident) * resident;
         bps = (target + nseg - 1) / nseg;
     }
     if (bps > ntiles) bps = ntiles;
