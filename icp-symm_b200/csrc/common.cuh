@@ -46,6 +46,7 @@ struct TreeShape {
     uint32_t level_off[ICP_MAX_LEVELS];   // offset of level l (>= 1) inside a segment's record array
     uint32_t level_cnt[ICP_MAX_LEVELS];   // padded node count of level l (multiple of ICP_FAN, root = 1)
     uint32_t nodes_per_seg;               // records per segment = sum of level_cnt[1..]
+    uint32_t units_per_seg;               // 32-point units per segment = ceil(pitch / 32)
 };
 
 // device view of a cloud set
@@ -54,6 +55,7 @@ struct CloudView {
     const float4* nrm;
     const WideNode* nodes;
     const uint32_t* pos_of_orig;          // seg*P + original index -> sorted position
+    const uint32_t* unit_split;           // seg*units_per_seg + unit: lane mask of the second cluster of a split unit, else 0
     const uint32_t* counts;               // points per segment
     TreeShape shape;
     uint32_t nseg;

@@ -269,6 +269,55 @@ __global__ void __launch_bounds__(256) inverse_perm_kernel(const float4* __restr
     pos_of_orig[(size_t)seg * pitch + __float_as_uint(pts[j].w)] = i;
 }
 
+// ---- split units ------------------------------------------------------------------------------
+// A unit is 32 consecutive sorted points: the 32 queries one warp searches together.  The curve leaves
+// and re-enters a surface, so about one unit in a hundred holds two clusters that lie far apart; its
+// warp would pay for the union of two unrelated search regions with half of its lanes idle in each.
+// Such a unit is marked here (once per cloud) with the lane mask of its second cluster and the kNN search
+// of the normal estimation walks the hierarchy once per cluster (normals of 1M points: -6 %, and no more
+// straggler blocks at the end of the kernel).  Split = cut at the middle of the longest axis leaves two
+// groups that are each at most 0.4x as wide as the unit (2-4 % of the units of a scanned surface).
+#ifndef ICP_SPLIT_RATIO2
+#define ICP_SPLIT_RATIO2 6.f    // (unit width / group width)^2 from which a unit counts as two clusters (swept: 4..9 equal, 2 and 16 worse)
+#endif
+__global__ void __launch_bounds__(256) unit_split_kernel(const float4* __restrict__ pts, const uint32_t* __restrict__ counts,
+                                                         uint32_t pitch, uint32_t units_per_seg, uint32_t nseg,
+                                                         uint32_t* __restrict__ unit_split) {
+    const size_t wid = ((size_t)blockIdx.x * 256 + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    if (wid >= (size_t)nseg * units_per_seg) return;
+    const uint32_t seg = (uint32_t)(wid / units_per_seg), unit = (uint32_t)(wid - (size_t)seg * units_per_seg);
+    const uint32_t i = unit * 32u + lane;
+    const bool act = i < counts[seg] && i < pitch;
+    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (act) p = pts[(size_t)seg * pitch + i];
+    const uint32_t none_lo = 0xffffffffu, none_hi = 0u;
+    uint32_t ox = float_to_ordered(p.x), oy = float_to_ordered(p.y), oz = float_to_ordered(p.z);
+    const float lx = ordered_to_float(__reduce_min_sync(0xffffffffu, act ? ox : none_lo)), hx = ordered_to_float(__reduce_max_sync(0xffffffffu, act ? ox : none_hi));
+    const float ly = ordered_to_float(__reduce_min_sync(0xffffffffu, act ? oy : none_lo)), hy = ordered_to_float(__reduce_max_sync(0xffffffffu, act ? oy : none_hi));
+    const float lz = ordered_to_float(__reduce_min_sync(0xffffffffu, act ? oz : none_lo)), hz = ordered_to_float(__reduce_max_sync(0xffffffffu, act ? oz : none_hi));
+    uint32_t mask = 0u;
+    if (__popc(__ballot_sync(0xffffffffu, act)) >= 2) {
+        const float ex = hx - lx, ey = hy - ly, ez = hz - lz;
+        const float c = (ex >= ey && ex >= ez) ? p.x : (ey >= ez ? p.y : p.z);
+        const float mid = (ex >= ey && ex >= ez) ? 0.5f * (lx + hx) : (ey >= ez ? 0.5f * (ly + hy) : 0.5f * (lz + hz));
+        const bool g1 = act && c > mid, g0 = act && !g1;
+        float d2[2];
+#pragma unroll
+        for (int g = 0; g < 2; g++) {
+            const bool in = g ? g1 : g0;
+            const float ax = ordered_to_float(__reduce_max_sync(0xffffffffu, in ? ox : none_hi)) - ordered_to_float(__reduce_min_sync(0xffffffffu, in ? ox : none_lo));
+            const float ay = ordered_to_float(__reduce_max_sync(0xffffffffu, in ? oy : none_hi)) - ordered_to_float(__reduce_min_sync(0xffffffffu, in ? oy : none_lo));
+            const float az = ordered_to_float(__reduce_max_sync(0xffffffffu, in ? oz : none_hi)) - ordered_to_float(__reduce_min_sync(0xffffffffu, in ? oz : none_lo));
+            d2[g] = ax * ax + ay * ay + az * az;   // an empty group gives +inf - -inf... guarded below
+        }
+        const uint32_t m1 = __ballot_sync(0xffffffffu, g1), m0 = __ballot_sync(0xffffffffu, g0);
+        const float whole = ex * ex + ey * ey + ez * ez;
+        if (m0 && m1 && fmaxf(d2[0], d2[1]) * ICP_SPLIT_RATIO2 < whole) mask = m1;
+    }
+    if (lane == 0) unit_split[(size_t)seg * units_per_seg + unit] = mask;
+}
+
 __device__ __forceinline__ void store_child_box(WideNode* __restrict__ rec, uint32_t slot, float3 lo, float3 hi) {
     rec->lox[slot] = lo.x; rec->loy[slot] = lo.y; rec->loz[slot] = lo.z;
     rec->hix[slot] = hi.x; rec->hiy[slot] = hi.y; rec->hiz[slot] = hi.z;
@@ -393,11 +442,12 @@ TreeShape icp_make_shape(uint32_t max_count) {
     }
     sh.n_levels = (cnt > 1) ? 0 : l + 1;   // 0 = too many points for ICP_MAX_LEVELS
     sh.nodes_per_seg = off ? off : 1;
+    sh.units_per_seg = (sh.pitch + 31u) / 32u;
     return sh;
 }
 
 void icp_free_cloudset(CloudSet& cs) {
-    cudaFree(cs.pts); cudaFree(cs.nrm); cudaFree(cs.nodes); cudaFree(cs.pos_of_orig); cudaFree(cs.counts);
+    cudaFree(cs.pts); cudaFree(cs.nrm); cudaFree(cs.nodes); cudaFree(cs.unit_split); cudaFree(cs.pos_of_orig); cudaFree(cs.counts);
     cudaFree(cs.bbox); cudaFree(cs.bb_lo); cudaFree(cs.bb_hi);
     free(cs.h_counts);
     cs = CloudSet();
@@ -432,6 +482,7 @@ int icp_build_cloudset(icpsymm_ctx* ctx, CloudSet& cs, const float* xyz, bool on
     cap = cs.cap_pts;  if ((rc = icp_reserve(ctx, &cs.pos_of_orig, &cap, slots))) return rc;
     cs.cap_pts = cap;
     if ((rc = icp_reserve(ctx, &cs.nodes, &cs.cap_nodes, nodes))) return rc;
+    if ((rc = icp_reserve(ctx, &cs.unit_split, &cs.cap_units, nseg * (size_t)sh.units_per_seg))) return rc;
     cap = cs.cap_seg;  if ((rc = icp_reserve(ctx, &cs.counts, &cap, nseg))) return rc;
     cap = cs.cap_seg * 8; if ((rc = icp_reserve(ctx, &cs.bbox, &cap, nseg * 8))) return rc;
     cap = cs.cap_seg;  if ((rc = icp_reserve(ctx, &cs.bb_lo, &cap, nseg))) return rc;
@@ -489,6 +540,10 @@ int icp_build_cloudset(icpsymm_ctx* ctx, CloudSet& cs, const float* xyz, bool on
         if (wins) kd_refine_kernel<<<ns * wins, kKdWindow / 2, 0, st>>>(cs.pts, cs.counts, sh.pitch, wins);
     }
     inverse_perm_kernel<<<gb, 256, 0, st>>>(cs.pts, cs.counts, sh.pitch, ns, cs.pos_of_orig);
+    {
+        size_t thr = (size_t)ns * sh.units_per_seg * 32;
+        unit_split_kernel<<<(uint32_t)((thr + 255) / 256), 256, 0, st>>>(cs.pts, cs.counts, sh.pitch, sh.units_per_seg, ns, cs.unit_split);
+    }
     {
         size_t nfl = nodes * 48;
         init_nodes_kernel<<<(uint32_t)((nfl + 255) / 256), 256, 0, st>>>(cs.nodes, nfl);

@@ -17,6 +17,8 @@ struct CloudSet {
     float4* nrm = nullptr;
     WideNode* nodes = nullptr;
     uint32_t* pos_of_orig = nullptr;
+    uint32_t* unit_split = nullptr;   // per 32-point unit: lane mask of its second cluster (0 = compact unit)
+    size_t cap_units = 0;
     uint32_t* counts = nullptr;   // device, nseg
     uint32_t* bbox = nullptr;     // device, nseg*8 ordered-uint (lo xyz, pad, hi xyz, pad) during build
     float4* bb_lo = nullptr;      // device, nseg
@@ -30,7 +32,7 @@ struct CloudSet {
 
     CloudView view() const {
         CloudView v;
-        v.pts = pts; v.nrm = nrm; v.nodes = nodes; v.pos_of_orig = pos_of_orig; v.counts = counts;
+        v.pts = pts; v.nrm = nrm; v.nodes = nodes; v.pos_of_orig = pos_of_orig; v.unit_split = unit_split; v.counts = counts;
         v.shape = shape; v.nseg = nseg;
         return v;
     }

@@ -11,6 +11,37 @@
 #include "internal.h"
 #include "search.cuh"
 
+#ifdef ICP_BLOCK_TIMES
+__device__ unsigned long long icp_blk_times[3 * 65536];
+struct BlockTimer {
+    unsigned long long t0;
+    __device__ BlockTimer() { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0)); }
+    __device__ ~BlockTimer() {
+        __syncthreads();
+        if (threadIdx.x == 0 && blockIdx.x < 65536) {
+            unsigned long long t1; unsigned int sm;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+            icp_blk_times[3 * blockIdx.x] = t0; icp_blk_times[3 * blockIdx.x + 1] = t1; icp_blk_times[3 * blockIdx.x + 2] = sm;
+        }
+    }
+};
+extern "C" int icpsymm_debug_sorted_points(icpsymm_ctx* ctx, int which, float* out, size_t n) {
+    cudaDeviceSynchronize();
+    const CloudSet& cs = which ? ctx->tgt : ctx->src;
+    return (int)cudaMemcpy(out, cs.pts, n * sizeof(float4), cudaMemcpyDeviceToHost);
+}
+extern "C" int icpsymm_debug_unit_split(icpsymm_ctx* ctx, int which, uint32_t* out, size_t n) {
+    cudaDeviceSynchronize();
+    const CloudSet& cs = which ? ctx->tgt : ctx->src;
+    return (int)cudaMemcpy(out, cs.unit_split, n * sizeof(uint32_t), cudaMemcpyDeviceToHost);
+}
+extern "C" int icpsymm_debug_block_times(unsigned long long* out, int n) {
+    cudaDeviceSynchronize();
+    return (int)cudaMemcpyFromSymbol(out, icp_blk_times, sizeof(unsigned long long) * 3 * n);
+}
+#endif
+
 namespace {
 
 struct NormalParams {
@@ -38,8 +69,12 @@ __device__ __forceinline__ void jacobi_rotate(float& app, float& aqq, float& apq
     }
 }
 
+
 template <int KMAX, bool EXACT>
 __global__ void __launch_bounds__(128, (KMAX <= 16) ? 7 : 4) normals_kernel(const __grid_constant__ NormalParams P) {
+#ifdef ICP_BLOCK_TIMES
+    BlockTimer bt_;
+#endif
     // one block = 128 consecutive sorted points of ONE segment, so that a warp never straddles two
     // clouds and its 32 lanes can walk the hierarchy together
     const uint32_t pitch = P.cloud.shape.pitch;
@@ -79,7 +114,9 @@ __global__ void __launch_bounds__(128, (KMAX <= 16) ? 7 : 4) normals_kernel(cons
             }
         }
     }
-    knn_traverse_warp<KMAX, EXACT>(P.cloud.shape, boxes, pts, q.x, q.y, q.z, k, g_lo, g_hi, active, L);
+    // warp-uniform: blocks start at multiples of 128 points, so a warp is exactly one 32-point unit
+    const uint32_t split = __ldg(P.cloud.unit_split + (size_t)seg * P.cloud.shape.units_per_seg + (i >> 5));
+    knn_traverse_warp<KMAX, EXACT>(P.cloud.shape, boxes, pts, q.x, q.y, q.z, k, g_lo, g_hi, active, split, L);
     if (!active) return;
 
     // covariance of the neighbourhood (the parked k nearest), coordinates relative to the query point

@@ -178,8 +178,8 @@ __device__ __forceinline__ bool warp_child_recheck(const WideNode* __restrict__ 
 }
 
 template <typename V>
-__device__ __forceinline__ void wide_traverse_warp(const TreeShape& sh, const WideNode* __restrict__ seg_nodes,
-                                                   float qx, float qy, float qz, bool active, V& v) {
+__device__ __forceinline__ void wide_traverse_group(const TreeShape& sh, const WideNode* __restrict__ seg_nodes,
+                                                    float qx, float qy, float qz, bool active, V& v) {
     const int top = (int)sh.n_levels - 1;
     if (top == 0) { v.leaf(0); return; }
     if (!__any_sync(0xffffffffu, active)) return;
@@ -232,11 +232,27 @@ __device__ __forceinline__ void wide_traverse_warp(const TreeShape& sh, const Wi
     }
 }
 
+// split_mask != 0 (warp-uniform): the unit holds two far-apart clusters (index build, unit_split_kernel);
+// the lanes of each cluster walk the hierarchy on their own, so that each walk sees a compact patch.
+template <typename V>
+__device__ __forceinline__ void wide_traverse_warp(const TreeShape& sh, const WideNode* __restrict__ seg_nodes,
+                                                   float qx, float qy, float qz, bool active, uint32_t split_mask, V& v) {
+    const bool second = (split_mask >> (threadIdx.x & 31)) & 1u;
+    const int passes = split_mask ? 2 : 1;
+#pragma unroll 1
+    for (int pass = 0; pass < passes; pass++) {
+        const bool act = active && (passes == 1 || second == (pass == 1));
+        v.set_active(act);
+        wide_traverse_group(sh, seg_nodes, qx, qy, qz, act, v);
+    }
+}
+
 struct NNVisitor {
     Best& b;
     const float4* __restrict__ pts;
     float qx, qy, qz;
     __device__ __forceinline__ uint32_t bound_bits() const { return (uint32_t)(b.key >> 32); }
+    __device__ __forceinline__ void set_active(bool) {}   // a bystander lane only collects valid candidates
     __device__ __forceinline__ void leaf(uint32_t g) { scan_leaf(pts, g, qx, qy, qz, b); }
 };
 
@@ -244,9 +260,9 @@ struct NNVisitor {
 // Must be called by all 32 lanes; lanes without a query pass active = false.
 __device__ __forceinline__ void nn_traverse_warp(const TreeShape& sh, const WideNode* __restrict__ seg_nodes,
                                                  const float4* __restrict__ seg_pts, float qx, float qy, float qz,
-                                                 bool active, Best& b) {
+                                                 bool active, uint32_t split_mask, Best& b) {
     NNVisitor v{b, seg_pts, qx, qy, qz};
-    wide_traverse_warp(sh, seg_nodes, qx, qy, qz, active, v);
+    wide_traverse_warp(sh, seg_nodes, qx, qy, qz, active, split_mask, v);
 }
 
 // ---- k nearest ------------------------------------------------------------------------------
@@ -373,6 +389,7 @@ struct KnnVisitor {
     uint32_t g_lo, g_hi;
     bool active;
     __device__ __forceinline__ uint32_t bound_bits() const { return L.bound_bits(); }
+    __device__ __forceinline__ void set_active(bool a) { active = a; }   // a bystander must not park candidates
     __device__ __forceinline__ void leaf(uint32_t g) {
         // warp-uniform call; a lane sits out the leaves it has already seen
         knn_offer_leaf(L, pts, g, qx, qy, qz, active && !(g >= g_lo && g <= g_hi));
@@ -384,11 +401,11 @@ struct KnnVisitor {
 template <int KMAX, bool EXACT>
 __device__ __forceinline__ void knn_traverse_warp(const TreeShape& sh, const WideNode* __restrict__ seg_nodes,
                                                   const float4* __restrict__ seg_pts, float qx, float qy, float qz,
-                                                  int k, uint32_t g_lo, uint32_t g_hi, bool active,
+                                                  int k, uint32_t g_lo, uint32_t g_hi, bool active, uint32_t split_mask,
                                                   KList<KMAX, EXACT>& L) {
     KnnVisitor<KMAX, EXACT> v{L, seg_pts, qx, qy, qz, k, g_lo, g_hi, active};
     L.flush(k);                                   // the caller's window scan
-    wide_traverse_warp(sh, seg_nodes, qx, qy, qz, active, v);
+    wide_traverse_warp(sh, seg_nodes, qx, qy, qz, active, split_mask, v);
     L.flush(k);
     L.compact(k, seg_pts);
 }
