@@ -24,6 +24,26 @@
 #include "internal.h"
 #include "search.cuh"
 
+#ifdef ICP_BLOCK_TIMES   // developer instrumentation: per-block start/end/SM of the last K1 launch
+__device__ unsigned long long icp_k1_times[3 * 8192];
+struct K1Timer {
+    unsigned long long t0;
+    __device__ K1Timer() { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0)); }
+    __device__ void stop() {
+        if (threadIdx.x == 0 && blockIdx.x < 8192) {
+            unsigned long long t1; unsigned int sm;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+            icp_k1_times[3 * blockIdx.x] = t0; icp_k1_times[3 * blockIdx.x + 1] = t1; icp_k1_times[3 * blockIdx.x + 2] = sm;
+        }
+    }
+};
+extern "C" int icpsymm_debug_k1_times(unsigned long long* out, int n) {
+    cudaDeviceSynchronize();
+    return (int)cudaMemcpyFromSymbol(out, icp_k1_times, sizeof(unsigned long long) * 3 * n);
+}
+#endif
+
 namespace {
 
 constexpr int kNNThreads = 256;
@@ -98,6 +118,9 @@ __global__ void init_state_kernel(SegState* state, uint32_t nseg, InitArgs a, co
 // K1: search + accumulate
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kNNThreads, 4) nn_accum_kernel(const __grid_constant__ NNParams P) {
+#ifdef ICP_BLOCK_TIMES
+    K1Timer timer_;
+#endif
     const uint32_t seg = blockIdx.x / P.blocks_per_seg;
     const uint32_t blk = blockIdx.x - seg * P.blocks_per_seg;
     const SegState* st = P.state + seg;
@@ -225,6 +248,9 @@ __global__ void __launch_bounds__(kNNThreads, 4) nn_accum_kernel(const __grid_co
         for (int w = 0; w < kNNWarps; w++) s += wacc[w][tid];
         P.partial[((size_t)seg * P.blocks_per_seg + blk) * ICP_PART_STRIDE + tid] = s;
     }
+#ifdef ICP_BLOCK_TIMES
+    timer_.stop();
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -88,21 +88,15 @@ __global__ void __launch_bounds__(128, (KMAX <= 16) ? 7 : 4) normals_kernel(cons
     const float4 q = active ? ldg4(pts + i) : make_float4(0.f, 0.f, 0.f, 0.f);
     const int k = P.k;
 
-    // first bound: the query's own leaf group and its neighbours along the curve
     typedef KList<KMAX, EXACT> List;
     __shared__ unsigned long long s_park[List::CAP][128];   // [slot][thread]: conflict-free columns
     List L;
     L.init(&s_park[0][threadIdx.x], 128);
     const uint32_t n_groups = pitch / ICP_LEAF;
-#ifdef ICP_KNN_CELL_WINDOW
-    // the aligned 64-point (k <= 16) or 128-point cell that holds the query: a k-d cell of the refined order
+    // first bound: the aligned 64-point (k <= 16) or 128-point cell that holds the query -- a k-d cell of the refined order
     const uint32_t g = active ? i / ICP_LEAF : 0u, w = (k <= 16) ? 8u : 16u;
     const uint32_t g_lo = g / w * w, g_hi = (g_lo + w - 1 < n_groups) ? g_lo + w - 1 : n_groups - 1;
-#else
-    const uint32_t g = active ? i / ICP_LEAF : 0u, w = (k <= 16) ? 1u : 2u;
-    const uint32_t g_lo = g >= w ? g - w : 0u, g_hi = (g + w < n_groups) ? g + w : n_groups - 1;
-#endif
-    // lanes of one warp cover at most 5 consecutive leaf groups; walk the union of their windows
+    // the 32 lanes of a warp share the cell: every lane takes all of its leaf groups
     {
         const uint32_t w_lo = __reduce_min_sync(0xffffffffu, active ? g_lo : 0xffffffffu);
         const uint32_t w_hi = __reduce_max_sync(0xffffffffu, active ? g_hi : 0u);
