@@ -16,7 +16,6 @@
 
 namespace {
 
-constexpr uint32_t kPadKey = 0x40000000u;  // sorts after every 30-bit curve index
 
 __global__ void bbox_init_kernel(uint32_t* bbox, uint32_t nseg, int* flags) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -83,13 +82,13 @@ __device__ __forceinline__ uint32_t spread10(uint32_t v) {  // 10 bits -> every 
     return v;
 }
 
-// 30-bit Hilbert index of a 10-bit cell coordinate (Skilling's transpose algorithm).  Hilbert order
-// keeps every run of consecutive points spatially compact, so the boxes of the implicit 8-ary
-// hierarchy overlap far less than under Z-order (measured: ~1.5x fewer node visits per query).
-__device__ __forceinline__ uint32_t hilbert30(uint32_t x, uint32_t y, uint32_t z) {
+// Hilbert index (3*bits wide) of a cell coordinate of `bits` bits per axis (Skilling's transpose
+// algorithm).  Hilbert order keeps every run of consecutive points spatially compact, so the boxes of
+// the implicit 8-ary hierarchy overlap far less than under Z-order (measured: ~1.5x fewer node visits
+// per query).
+__device__ __forceinline__ uint32_t hilbert_index(uint32_t x, uint32_t y, uint32_t z, int bits) {
     uint32_t X[3] = {x, y, z};
-#pragma unroll
-    for (uint32_t Q = 512u; Q > 1u; Q >>= 1) {
+    for (uint32_t Q = 1u << (bits - 1); Q > 1u; Q >>= 1) {
         const uint32_t Pm = Q - 1u;
 #pragma unroll
         for (int i = 0; i < 3; i++) {
@@ -100,8 +99,7 @@ __device__ __forceinline__ uint32_t hilbert30(uint32_t x, uint32_t y, uint32_t z
     X[1] ^= X[0];
     X[2] ^= X[1];
     uint32_t t = 0;
-#pragma unroll
-    for (uint32_t Q = 512u; Q > 1u; Q >>= 1)
+    for (uint32_t Q = 1u << (bits - 1); Q > 1u; Q >>= 1)
         if (X[2] & Q) t ^= Q - 1u;
     X[0] ^= t; X[1] ^= t; X[2] ^= t;
     return (spread10(X[0]) << 2) | (spread10(X[1]) << 1) | spread10(X[2]);
@@ -111,23 +109,26 @@ __device__ __forceinline__ uint32_t hilbert30(uint32_t x, uint32_t y, uint32_t z
 __global__ void __launch_bounds__(256) curve_key_kernel(const char* __restrict__ raw, size_t stride_bytes,
                                                      const uint32_t* __restrict__ counts, uint32_t max_count,
                                                      uint32_t pitch, uint32_t nseg, const float4* __restrict__ bb_lo,
-                                                     const float4* __restrict__ bb_hi,
+                                                     const float4* __restrict__ bb_hi, int bits,
                                                      unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals) {
     size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= (size_t)nseg * pitch) return;
     uint32_t seg = (uint32_t)(j / pitch), i = (uint32_t)(j - (size_t)seg * pitch);
-    uint32_t code = kPadKey;
+    // padding takes the largest index: the sort is stable and padding slots follow the real ones in the
+    // input, so they still end up last in their segment
+    const uint32_t cells = 1u << bits;
+    uint32_t code = (1u << (3 * bits)) - 1u;
     if (i < counts[seg]) {
         const float* p = reinterpret_cast<const float*>(raw + ((size_t)seg * max_count + i) * stride_bytes);
         float4 lo = bb_lo[seg], hi = bb_hi[seg];
         float ext = fmaxf(fmaxf(hi.x - lo.x, hi.y - lo.y), hi.z - lo.z);
-        float scale = ext > 0.f ? 1023.5f / ext : 0.f;
-        uint32_t cx = min(1023u, (uint32_t)((p[0] - lo.x) * scale));
-        uint32_t cy = min(1023u, (uint32_t)((p[1] - lo.y) * scale));
-        uint32_t cz = min(1023u, (uint32_t)((p[2] - lo.z) * scale));
-        code = hilbert30(cx, cy, cz);
+        float scale = ext > 0.f ? ((float)cells - 0.5f) / ext : 0.f;
+        uint32_t cx = min(cells - 1u, (uint32_t)((p[0] - lo.x) * scale));
+        uint32_t cy = min(cells - 1u, (uint32_t)((p[1] - lo.y) * scale));
+        uint32_t cz = min(cells - 1u, (uint32_t)((p[2] - lo.z) * scale));
+        code = hilbert_index(cx, cy, cz, bits);
     }
-    keys[j] = ((unsigned long long)seg << 32) | code;
+    keys[j] = ((unsigned long long)seg << (3 * bits)) | code;
     vals[j] = i;
 }
 
@@ -519,11 +520,19 @@ int icp_build_cloudset(icpsymm_ctx* ctx, CloudSet& cs, const float* xyz, bool on
     }
     bbox_finish_kernel<<<(ns + 127) / 128, 128, 0, st>>>(cs.bbox, cs.counts, cs.bb_lo, cs.bb_hi, ns);
     const uint32_t gb = (uint32_t)((slots + 255) / 256);
-    curve_key_kernel<<<gb, 256, 0, st>>>(raw, stride_bytes, cs.counts, mc, sh.pitch, ns, cs.bb_lo, cs.bb_hi,
+    // 10 bits per axis.  A coarser grid would do for the windows of the k-d refinement and saves a radix
+    // pass (8 bits: index build -36 us per 1M cloud), but the upper levels of the hierarchy get worse:
+    // loop +1.6 %, normals +1.4 % -- measured, not adopted.
+#ifdef ICP_CURVE_BITS
+    const int curve_bits = ICP_CURVE_BITS;
+#else
+    const int curve_bits = 10;
+#endif
+    curve_key_kernel<<<gb, 256, 0, st>>>(raw, stride_bytes, cs.counts, mc, sh.pitch, ns, cs.bb_lo, cs.bb_hi, curve_bits,
                                       B.keys_a, B.vals_a);
     int seg_bits = 0;
     while ((1ull << seg_bits) < nseg) seg_bits++;
-    int end_bit = (nseg > 1) ? 32 + seg_bits : 31;
+    int end_bit = 3 * curve_bits + seg_bits;
     size_t temp_bytes = 0;
     ICP_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, B.keys_a, B.keys_b, B.vals_a,
                                                    B.vals_b, slots, 0, end_bit, st));
