@@ -14,6 +14,15 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+// developer build (make EXTRA=-DICP_DEBUG_ASSERT): device-side bounds assertions on every index the
+// traversals derive from data; the memory-checking tools are not available on the GPU pool
+#ifdef ICP_DEBUG_ASSERT
+#include <cassert>
+#define ICP_ASSERT(c) assert(c)
+#else
+#define ICP_ASSERT(c) ((void)0)
+#endif
+
 #define ICP_LOG_LEAF 3
 #define ICP_LEAF (1 << ICP_LOG_LEAF)     // points per leaf group (8 * 16 B = one 128 B line)
 #define ICP_LOG_FAN 3

@@ -181,6 +181,7 @@ __global__ void __launch_bounds__(kNNThreads, 4) nn_accum_kernel(const __grid_co
                                       ? __ldg(P.tgt.pos_of_orig + (size_t)seg * P.tgt.shape.pitch + b.id())
                                       : 0xffffffffu;
             const float bd2 = b.d2();
+            ICP_ASSERT(bpos == 0xffffffffu || bpos < nt);
             corr[i] = bpos;
             if (bpos < nt) {
                 const float4 q = ldg4(tpts + bpos);

@@ -121,6 +121,7 @@ __global__ void __launch_bounds__(128, (KMAX <= 16) ? 7 : 4) normals_kernel(cons
     for (int t = 0; t < KMAX; t++) {
         ux[t] = uy[t] = uz[t] = 0.f;
         if (t < L.cnt) {
+            ICP_ASSERT((uint32_t)L.buf[t * L.stride] < cnt && L.cnt <= k);
             const float4 c = ldg4(pts + (uint32_t)L.buf[t * L.stride]);
             ux[t] = c.x - q.x; uy[t] = c.y - q.y; uz[t] = c.z - q.z;
             mx += ux[t]; my += uy[t]; mz += uz[t];

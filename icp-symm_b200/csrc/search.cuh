@@ -213,7 +213,9 @@ __device__ __forceinline__ void wide_traverse_group(const TreeShape& sh, const W
         const WideNode* rec = seg_nodes + sh.level_off[l] + i;
         if (((stale >> l) & 1u) && !warp_child_recheck(rec, c, qx, qy, qz, v.bound_bits(), active)) continue;
         const uint32_t child = (i << ICP_LOG_FAN) + (uint32_t)c;
+        ICP_ASSERT(l >= 1 && l <= top && i < sh.level_cnt[l] && child < sh.level_cnt[l - 1]);
         if (l == 1) {
+            ICP_ASSERT(child < sh.pitch / ICP_LEAF);
             const uint32_t before = v.bound_bits();
             v.leaf(child);
             const uint32_t after = v.bound_bits();
@@ -333,6 +335,7 @@ struct KList {
             }
         }
         // surplus ties at the k-th distance (rare): drop the largest original index until k remain
+        ICP_ASSERT(w <= CAP && w <= cnt);
         while (w > k) {
             int worst = 0;
             unsigned long long worst_key = 0ull;
@@ -372,6 +375,7 @@ __device__ __forceinline__ void knn_offer_leaf(KList<KMAX, EXACT>& L, const floa
 #pragma unroll
     for (int j = 0; j < ICP_LEAF; j++) {
         if (db[j] <= thr && take) {
+            ICP_ASSERT(L.cnt >= 0 && L.cnt < (KList<KMAX, EXACT>::CAP));
             L.buf[L.cnt * L.stride] = ((unsigned long long)db[j] << 32) | (g * ICP_LEAF + (uint32_t)j);
             L.cnt++;
         }
