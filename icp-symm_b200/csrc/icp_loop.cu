@@ -20,6 +20,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <cooperative_groups.h>
 
 #include "internal.h"
 #include "search.cuh"
@@ -38,18 +39,32 @@ struct K1Timer {
         }
     }
 };
+__device__ unsigned long long icp_k2_stamps[8];
+#define ICP_K2_STAMP(i) do { if (threadIdx.x == 0 && blockIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); icp_k2_stamps[i] = t_; } } while (0)
+extern "C" int icpsymm_debug_k2_stamps(unsigned long long* out) {
+    cudaDeviceSynchronize();
+    return (int)cudaMemcpyFromSymbol(out, icp_k2_stamps, sizeof(unsigned long long) * 8);
+}
 extern "C" int icpsymm_debug_k1_times(unsigned long long* out, int n) {
     cudaDeviceSynchronize();
     return (int)cudaMemcpyFromSymbol(out, icp_k1_times, sizeof(unsigned long long) * 3 * n);
 }
+#else
+#define ICP_K2_STAMP(i) do { } while (0)
 #endif
 
 namespace {
 
 constexpr int kNNThreads = 256;
 constexpr int kNNWarps = kNNThreads / 32;
-constexpr int kSolveThreads = 1024;
+#ifndef ICP_K2_THREADS
+#define ICP_K2_THREADS 1024
+#endif
+constexpr int kSolveThreads = ICP_K2_THREADS;
 constexpr int kSolveParts = kSolveThreads / ICP_NSUMS;  // 27
+#ifndef ICP_K2_BATCH
+#define ICP_K2_BATCH 16  // loads of the K2 row reduction issued back to back
+#endif
 
 struct NNParams {
     CloudView src, tgt;
@@ -424,40 +439,52 @@ __device__ __forceinline__ void loop_ctrl_arrive(const SolveParams& P, bool pair
     if (pair_done) atomicAdd(&P.ctrl->done_count, 1u);
     __threadfence();
     const unsigned int t = atomicAdd(&P.ctrl->ticket, 1u);
-    if (t == gridDim.x - 1) {
+    const unsigned int pairs = gridDim.x / cooperative_groups::this_cluster().num_blocks();   // one arrival per pair
+    if (t == pairs - 1) {
         const unsigned int done = atomicAdd(&P.ctrl->done_count, 0u);
         P.ctrl->ticket = 0u;
         P.ctrl->done_count = 0u;
-        cudaGraphSetConditional(P.cond, done < gridDim.x ? 1u : 0u);
+        cudaGraphSetConditional(P.cond, done < pairs ? 1u : 0u);
     }
 }
 
+// A pair with many partial rows (a single large pair) is reduced by a thread-block CLUSTER: one
+// block cannot pull rows out of L2 faster than ~100 GB/s, so the cn blocks of a cluster each add a
+// share of the rows, block 0 collects the cn partial vectors through distributed shared memory in
+// rank order, and goes on alone.  Batches of small pairs launch plain blocks (cluster of 1).
 __global__ void __launch_bounds__(kSolveThreads) solve_kernel(const __grid_constant__ SolveParams P) {
-    const uint32_t seg = blockIdx.x;
+    cooperative_groups::cluster_group cluster = cooperative_groups::this_cluster();
+    const uint32_t cn = cluster.num_blocks(), cr = cluster.block_rank();
+    const uint32_t seg = blockIdx.x / cn;
     SegState* st = P.state + seg;
     __shared__ double sPart[kSolveParts][ICP_NSUMS];
     __shared__ double sS[ICP_NSUMS];
     const int tid = threadIdx.x;
-    if (st->done) {
-        if (tid == 0) loop_ctrl_arrive(P, true);
+    ICP_K2_STAMP(0);
+    if (st->searches == 0) ICP_K2_STAMP(5);
+    if (st->done) {   // the same for every block of the cluster: all leave, nobody waits
+        if (tid == 0 && cr == 0) loop_ctrl_arrive(P, true);
         return;
     }
+    if (P.mode == 2 && cr != 0) return;   // solve-only launch: nothing to add up
     if (P.mode != 2) {
         const int v = tid % ICP_NSUMS, part = tid / ICP_NSUMS;
         if (part < kSolveParts) {
-            // part p adds rows p, p+27, p+54, ... in that order; 8 loads are issued back to back so the
-            // (L2-latency) loads overlap instead of serialising with the adds
+            // part g = cr*27 + p of the cn*27 parts adds rows g, g + 27 cn, g + 54 cn, ... in that order;
+            // ICP_K2_BATCH loads are issued back to back so the (L2-latency) loads overlap instead of
+            // serialising with the adds
             double s = 0.0;
             const double* row = P.partial + (size_t)seg * P.blocks_per_seg * ICP_PART_STRIDE + v;
-            uint32_t b = part;
-            for (; b + 7 * kSolveParts < P.blocks_per_seg; b += 8 * kSolveParts) {
-                double x[8];
+            const uint32_t step = kSolveParts * cn;
+            uint32_t b = cr * kSolveParts + part;
+            for (; b < P.blocks_per_seg; b += ICP_K2_BATCH * step) {
+                double x[ICP_K2_BATCH];   // rows past the end count as 0.0, which leaves the sum unchanged
 #pragma unroll
-                for (int u = 0; u < 8; u++) x[u] = row[(size_t)(b + u * kSolveParts) * ICP_PART_STRIDE];
+                for (int u = 0; u < ICP_K2_BATCH; u++)
+                    x[u] = (b + u * step < P.blocks_per_seg) ? row[(size_t)(b + u * step) * ICP_PART_STRIDE] : 0.0;
 #pragma unroll
-                for (int u = 0; u < 8; u++) s += x[u];
+                for (int u = 0; u < ICP_K2_BATCH; u++) s += x[u];
             }
-            for (; b < P.blocks_per_seg; b += kSolveParts) s += row[(size_t)b * ICP_PART_STRIDE];
             sPart[part][v] = s;
         }
         __syncthreads();
@@ -465,8 +492,19 @@ __global__ void __launch_bounds__(kSolveThreads) solve_kernel(const __grid_const
             double s = 0.0;
             for (int p = 0; p < kSolveParts; p++) s += sPart[p][tid];
             sS[tid] = s;
-            if (P.mode == 1 || P.mode == 3) P.gsum[(size_t)seg * ICP_PART_STRIDE + tid] = s;
         }
+        ICP_K2_STAMP(1);
+        if (cn > 1) {
+            cluster.sync();                         // every block's sS is complete
+            if (cr == 0 && tid < ICP_NSUMS) {
+                double s = sS[tid];
+                for (uint32_t r = 1; r < cn; r++) s += cluster.map_shared_rank(sS, r)[tid];
+                sS[tid] = s;
+            }
+            cluster.sync();                         // block 0 has read: the others may leave
+            if (cr != 0) return;
+        }
+        if (tid < ICP_NSUMS && (P.mode == 1 || P.mode == 3)) P.gsum[(size_t)seg * ICP_PART_STRIDE + tid] = sS[tid];
         __syncthreads();
         if (P.mode == 1) return;
         if (P.peer_world > 1) {
@@ -509,6 +547,7 @@ __global__ void __launch_bounds__(kSolveThreads) solve_kernel(const __grid_const
         __syncthreads();
     }
     if (tid != 0) return;
+    ICP_K2_STAMP(2);
 
     const LoopParams lp = *P.lp;
     const double diff = sS[33];
@@ -547,7 +586,9 @@ __global__ void __launch_bounds__(kSolveThreads) solve_kernel(const __grid_const
     for (int i = 0; i < 12; i++) { st->T[i] = Tn[i]; st->Tf[i] = (float)Tn[i]; }
     st->iter = st->iter + 1;
     st->pairs = (unsigned long long)(sS[36] + 0.5);
+    ICP_K2_STAMP(3);
     loop_ctrl_arrive(P, false);
+    ICP_K2_STAMP(4);
 }
 
 __global__ void solve_compose_kernel(const double* in /*37 sums + 3 origin*/, double* out /*12 T + 6 x + ratio + deg*/) {
@@ -633,6 +674,18 @@ static uint32_t choose_blocks_per_seg(const icpsymm_ctx* ctx, uint32_t nseg, uin
     return bps;
 }
 
+// one block per pair, or a cluster of 8 blocks per pair when there are many rows and few pairs
+static void launch_solve(const SolveParams& sp, uint32_t nseg, cudaStream_t st) {
+    const unsigned cn = (sp.blocks_per_seg >= 512u && nseg <= 16u) ? 8u : 1u;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(nseg * cn); cfg.blockDim = dim3(kSolveThreads); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cn; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, solve_kernel, sp);
+}
+
 static void launch_iteration(icpsymm_ctx* ctx, const NNParams& np, SolveParams sp, uint32_t nseg, bool use_comm,
                              cudaEvent_t* ev /*4 events or null*/) {
     cudaStream_t st = ctx->stream;
@@ -640,13 +693,13 @@ static void launch_iteration(icpsymm_ctx* ctx, const NNParams& np, SolveParams s
     nn_accum_kernel<<<nseg * np.blocks_per_seg, kNNThreads, 0, st>>>(np);
     if (ev) { cudaEventRecord(ev[1], st); cudaEventRecord(ev[2], st); }
     if (!use_comm) {
-        solve_kernel<<<nseg, kSolveThreads, 0, st>>>(sp);
+        launch_solve(sp, nseg, st);
     } else {
         sp.mode = 1;
-        solve_kernel<<<nseg, kSolveThreads, 0, st>>>(sp);
+        launch_solve(sp, nseg, st);
         icp_comm_allreduce(ctx, sp.gsum, (size_t)nseg * ICP_PART_STRIDE);
         sp.mode = 2;
-        solve_kernel<<<nseg, kSolveThreads, 0, st>>>(sp);
+        launch_solve(sp, nseg, st);
     }
     if (ev) cudaEventRecord(ev[3], st);
 }
