@@ -667,6 +667,12 @@ static uint32_t choose_blocks_per_seg(const icpsymm_ctx* ctx, uint32_t nseg, uin
         // best (1M points: 3907 tiles -> 2960 blocks, 5 % faster than 2368)
         if (nseg == 1 && ntiles > target && ntiles < 2u * target)
             target = ((ntiles * 3u / 4u + resident - 1u) / resident) * resident;
+        else if (nseg == 1 && ntiles >= 2u * target) {
+            // larger pairs: about 2.2 tiles per block in whole waves, at most 16 waves (4M points:
+            // 7104 blocks, 5 % faster than 2368; the cluster reduction of K2 makes the extra rows cheap)
+            target = ((ntiles * 9u / 20u + resident - 1u) / resident) * resident;
+            if (target > 16u * resident) target = 16u * resident;
+        }
         bps = (target + nseg - 1) / nseg;
     }
     if (bps > ntiles) bps = ntiles;
