@@ -674,6 +674,14 @@ static uint32_t choose_blocks_per_seg(const icpsymm_ctx* ctx, uint32_t nseg, uin
             if (target > 16u * resident) target = 16u * resident;
         }
         bps = (target + nseg - 1) / nseg;
+        if (nseg > 1) {
+            // batches: about 4 tiles per block (256 pairs of 32K points: 32 blocks per pair, 4 % faster than
+            // 10), as long as the grid stays below 32K blocks -- blocks of finished pairs only exit
+            uint32_t want = (ntiles + 3u) / 4u;
+            const uint32_t cap = 32768u / nseg;
+            if (want > cap) want = cap;
+            if (want > bps) bps = want;
+        }
     }
     if (bps > ntiles) bps = ntiles;
     if (bps < 1) bps = 1;
