@@ -70,8 +70,11 @@ __device__ __forceinline__ void jacobi_rotate(float& app, float& aqq, float& apq
 }
 
 
+#ifndef ICP_NRM_BLOCKS
+#define ICP_NRM_BLOCKS 7
+#endif
 template <int KMAX, bool EXACT>
-__global__ void __launch_bounds__(128, (KMAX <= 16) ? 7 : 4) normals_kernel(const __grid_constant__ NormalParams P) {
+__global__ void __launch_bounds__(128, (KMAX <= 16) ? ICP_NRM_BLOCKS : 4) normals_kernel(const __grid_constant__ NormalParams P) {
 #ifdef ICP_BLOCK_TIMES
     BlockTimer bt_;
 #endif

@@ -283,7 +283,10 @@ __device__ __forceinline__ void nn_traverse_warp(const TreeShape& sh, const Wide
 #define ICP_KNN_UNFILLED 0xfffffffeu     // above every distance, below the 0xffffffff of padding points
 template <int KMAX, bool EXACT>
 struct KList {
-    static constexpr int CAP = (KMAX <= 16) ? 32 : 48;   // parked candidates per lane (8 B each)
+#ifndef ICP_KNN_CAP
+#define ICP_KNN_CAP 32
+#endif
+    static constexpr int CAP = (KMAX <= 16) ? ICP_KNN_CAP : 48;   // parked candidates per lane (8 B each)
     uint32_t d[KMAX];
     uint32_t kth;              // d[k-1]: the current k-th smallest squared distance (bits)
     unsigned long long* buf;   // this lane's column: buf[slot * stride]
