@@ -163,30 +163,30 @@ __global__ void __launch_bounds__(256) init_nodes_kernel(WideNode* __restrict__ 
 // nodes (64) and the level-2 nodes (512) of a window become k-d cells: disjoint and tighter than
 // runs of the curve.  Measured on the 1M target: 20 % fewer leaf groups and 10 % fewer nodes reach a
 // warp of queries.  Results do not depend on the order (ties go by original index, carried in .w).
-constexpr uint32_t kKdWindow = 512;
-
+template <uint32_t kKdWindow>   // 256 .. 2048 points per window; kKdWindow / 2 threads, thread t owns elements t and t + kKdHalf
 __global__ void __launch_bounds__(kKdWindow / 2) kd_refine_kernel(float4* __restrict__ pts, const uint32_t* __restrict__ counts,
                                                                  uint32_t pitch, uint32_t wins_per_seg) {
+    constexpr uint32_t kKdHalf = kKdWindow / 2, kKdIdxMask = kKdWindow - 1;
     __shared__ float4 sp[kKdWindow];
     __shared__ uint32_t skey[kKdWindow];             // ordered coordinate, low 9 bits replaced by the element index
-    __shared__ uint32_t sbox[64][6];                 // per part: ordered-uint lo xyz, hi xyz
+    __shared__ uint32_t sbox[kKdWindow / ICP_LEAF][6];                 // per part: ordered-uint lo xyz, hi xyz
     const uint32_t seg = blockIdx.x / wins_per_seg, win = blockIdx.x - seg * wins_per_seg;
     const uint32_t base = win * kKdWindow;
     if (base + kKdWindow > counts[seg]) return;      // partial window (or padding): keep the curve order
     float4* gp = pts + (size_t)seg * pitch + base;
-    const uint32_t t = threadIdx.x;                  // 256 threads, elements t and t + 256
+    const uint32_t t = threadIdx.x;                  // kKdHalf threads, elements t and t + kKdHalf
     sp[t] = gp[t];
-    sp[t + 256] = gp[t + 256];
+    sp[t + kKdHalf] = gp[t + kKdHalf];
     __syncthreads();
     for (uint32_t S = kKdWindow; S > ICP_LEAF; S >>= 1) {       // part size at this split level
         const uint32_t parts = kKdWindow / S;
-        for (uint32_t v = t; v < parts * 6; v += 256) sbox[v / 6][v % 6] = (v % 6 < 3) ? 0xffffffffu : 0u;
+        for (uint32_t v = t; v < parts * 6; v += kKdHalf) sbox[v / 6][v % 6] = (v % 6 < 3) ? 0xffffffffu : 0u;
         __syncthreads();
         // bounding box of every part: the 32 elements of a warp lie in one part while S >= 32
         // (one REDUX per component, one shared atomic per warp); below that, 16 elements per part
 #pragma unroll
         for (int h = 0; h < 2; h++) {
-            const uint32_t e = t + 256 * h, part = e / S;
+            const uint32_t e = t + kKdHalf * h, part = e / S;
             const float4 p = sp[e];
             uint32_t ox = float_to_ordered(p.x), oy = float_to_ordered(p.y), oz = float_to_ordered(p.z);
             if (S >= 32) {
@@ -207,24 +207,24 @@ __global__ void __launch_bounds__(kKdWindow / 2) kd_refine_kernel(float4* __rest
         __syncthreads();
 #pragma unroll
         for (int h = 0; h < 2; h++) {
-            const uint32_t e = t + 256 * h, part = e / S;
+            const uint32_t e = t + kKdHalf * h, part = e / S;
             const float ex = ordered_to_float(sbox[part][3]) - ordered_to_float(sbox[part][0]);
             const float ey = ordered_to_float(sbox[part][4]) - ordered_to_float(sbox[part][1]);
             const float ez = ordered_to_float(sbox[part][5]) - ordered_to_float(sbox[part][2]);
             const float4 p = sp[e];
             const float c = (ex >= ey && ex >= ez) ? p.x : (ey >= ez ? p.y : p.z);
             // 23 bits of the coordinate are plenty to find a median; the index makes the keys unique
-            skey[e] = (float_to_ordered(c) & ~0x1ffu) | e;
+            skey[e] = (float_to_ordered(c) & ~kKdIdxMask) | e;
         }
         __syncthreads();
         // bitonic sort inside every part (parts are aligned powers of two; keys are unique).  Thread t
         // keeps the keys of elements t and t+256 in registers: partners at distance 256 are the
         // thread's own pair, distances below 32 are exchanged with warp shuffles, only distances
         // 32..128 go through shared memory (19 of the 155 steps of all six levels)
-        uint32_t v0 = skey[t], v1 = skey[t + 256];
+        uint32_t v0 = skey[t], v1 = skey[t + kKdHalf];
         for (uint32_t k = 2; k <= S; k <<= 1) {
             for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-                if (j == 256) {                       // k == 512 == S: ascending, element t is the low one
+                if (j == kKdHalf) {                   // k == kKdWindow == S: ascending, element t is the low one
                     const uint32_t lo = min(v0, v1), hi = max(v0, v1);
                     v0 = lo; v1 = hi;
                     continue;
@@ -232,9 +232,9 @@ __global__ void __launch_bounds__(kKdWindow / 2) kd_refine_kernel(float4* __rest
                 uint32_t p0, p1;
                 if (j >= 32) {
                     __syncthreads();
-                    skey[t] = v0; skey[t + 256] = v1;
+                    skey[t] = v0; skey[t + kKdHalf] = v1;
                     __syncthreads();
-                    p0 = skey[t ^ j]; p1 = skey[(t ^ j) + 256];
+                    p0 = skey[t ^ j]; p1 = skey[(t ^ j) + kKdHalf];
                 } else {
                     p0 = __shfl_xor_sync(0xffffffffu, v0, (int)j);
                     p1 = __shfl_xor_sync(0xffffffffu, v1, (int)j);
@@ -242,23 +242,156 @@ __global__ void __launch_bounds__(kKdWindow / 2) kd_refine_kernel(float4* __rest
                 // element e keeps the smaller key when it is the low partner of an ascending pair or the
                 // high partner of a descending one
                 const bool is_lo = (t & j) == 0;
-                const bool up0 = ((t & k) == 0) || (k == S), up1 = (((t + 256) & k) == 0) || (k == S);
+                const bool up0 = ((t & k) == 0) || (k == S), up1 = (((t + kKdHalf) & k) == 0) || (k == S);
                 v0 = (is_lo == up0) ? min(v0, p0) : max(v0, p0);
                 v1 = (is_lo == up1) ? min(v1, p1) : max(v1, p1);
             }
         }
         __syncthreads();
-        skey[t] = v0; skey[t + 256] = v1;
+        skey[t] = v0; skey[t + kKdHalf] = v1;
         __syncthreads();
         // permute the payload
-        const float4 a = sp[skey[t] & 0x1ffu], b = sp[skey[t + 256] & 0x1ffu];
+        const float4 a = sp[skey[t] & kKdIdxMask], b = sp[skey[t + kKdHalf] & kKdIdxMask];
         __syncthreads();
         sp[t] = a;
-        sp[t + 256] = b;
+        sp[t + kKdHalf] = b;
         __syncthreads();
     }
     gp[t] = sp[t];
-    gp[t + 256] = sp[t + 256];
+    gp[t + kKdHalf] = sp[t + kKdHalf];
+}
+
+// ---- coarse k-d splits of large windows ---------------------------------------------------------
+// The refinement above sorts, which costs log^2 steps and is limited to what two elements per
+// thread hold.  Above it only the PARTITION matters: every aligned window of W points is split at the
+// median of its longest axis into two halves, the halves again, ... down to parts of kKdFine points
+// (then kd_refine_kernel takes over).  A split level is an exact radix select of the median key in
+// shared memory (4 rounds of 8 bits, one histogram per part) and a stable partition (block-wide prefix
+// sums), so its cost does not grow with the part size.  Ties at the median go low in curve order.
+// 1024 threads own W / 1024 elements each (element e = k * 1024 + t); parts are at least 1024 points,
+// so the 1024 elements of one k all lie in the same part.
+constexpr uint32_t kKdFine = 512;
+template <uint32_t W>
+__global__ void __launch_bounds__(1024) kd_coarse_kernel(float4* __restrict__ pts, const uint32_t* __restrict__ counts,
+                                                         uint32_t pitch, uint32_t wins_per_seg) {
+    constexpr uint32_t E = W / 1024, MAXP = W / (2 * kKdFine);
+    extern __shared__ __align__(16) unsigned char kd_smem[];
+    float4* sp = reinterpret_cast<float4*>(kd_smem);
+    uint32_t* skey = reinterpret_cast<uint32_t*>(sp + W);
+    __shared__ uint32_t sbox[MAXP][6];
+    __shared__ uint32_t shist[MAXP][256];
+    __shared__ uint32_t s_prefix[MAXP], s_rank[MAXP];       // radix select state per part
+    __shared__ uint32_t s_warp[32][2], s_carry[MAXP][2];    // partition scan: per-warp counts, running counts per part
+    const uint32_t seg = blockIdx.x / wins_per_seg, win = blockIdx.x - seg * wins_per_seg;
+    const uint32_t base = win * W;
+    if (base + W > counts[seg]) return;                      // partial window: left to the curve order + fine refinement
+    float4* gp = pts + (size_t)seg * pitch + base;
+    const uint32_t t = threadIdx.x, lane = t & 31, warp = t >> 5;
+#pragma unroll
+    for (uint32_t k = 0; k < E; k++) sp[k * 1024 + t] = gp[k * 1024 + t];
+    __syncthreads();
+    for (uint32_t S = W; S > kKdFine; S >>= 1) {
+        const uint32_t parts = W / S;
+        for (uint32_t v = t; v < parts * 6; v += 1024) sbox[v / 6][v % 6] = (v % 6 < 3) ? 0xffffffffu : 0u;
+        if (t < parts) { s_prefix[t] = 0u; s_rank[t] = S / 2 - 1; s_carry[t][0] = 0u; s_carry[t][1] = 0u; }
+        __syncthreads();
+        // bounding box of every part
+#pragma unroll
+        for (uint32_t k = 0; k < E; k++) {
+            const float4 p = sp[k * 1024 + t];
+            const uint32_t part = (k * 1024) / S;
+            const uint32_t ox = float_to_ordered(p.x), oy = float_to_ordered(p.y), oz = float_to_ordered(p.z);
+            const uint32_t lx = __reduce_min_sync(0xffffffffu, ox), hx = __reduce_max_sync(0xffffffffu, ox);
+            const uint32_t ly = __reduce_min_sync(0xffffffffu, oy), hy = __reduce_max_sync(0xffffffffu, oy);
+            const uint32_t lz = __reduce_min_sync(0xffffffffu, oz), hz = __reduce_max_sync(0xffffffffu, oz);
+            if (lane == 0) {
+                atomicMin(&sbox[part][0], lx); atomicMax(&sbox[part][3], hx);
+                atomicMin(&sbox[part][1], ly); atomicMax(&sbox[part][4], hy);
+                atomicMin(&sbox[part][2], lz); atomicMax(&sbox[part][5], hz);
+            }
+        }
+        __syncthreads();
+        // keys: the coordinate along the longest axis of the part
+        uint32_t key[E];
+#pragma unroll
+        for (uint32_t k = 0; k < E; k++) {
+            const uint32_t part = (k * 1024) / S;
+            const float ex = ordered_to_float(sbox[part][3]) - ordered_to_float(sbox[part][0]);
+            const float ey = ordered_to_float(sbox[part][4]) - ordered_to_float(sbox[part][1]);
+            const float ez = ordered_to_float(sbox[part][5]) - ordered_to_float(sbox[part][2]);
+            const float4 p = sp[k * 1024 + t];
+            key[k] = float_to_ordered((ex >= ey && ex >= ez) ? p.x : (ey >= ez ? p.y : p.z));
+        }
+        // exact median key of every part: radix select, most significant byte first
+        for (int shift = 24; shift >= 0; shift -= 8) {
+            for (uint32_t v = t; v < parts * 256; v += 1024) shist[v >> 8][v & 255] = 0u;
+            __syncthreads();
+            const uint32_t mask = (shift == 24) ? 0u : (0xffffffffu << (shift + 8));
+#pragma unroll
+            for (uint32_t k = 0; k < E; k++) {
+                const uint32_t part = (k * 1024) / S;
+                if ((key[k] & mask) == s_prefix[part]) atomicAdd(&shist[part][(key[k] >> shift) & 255u], 1u);
+            }
+            __syncthreads();
+            if (warp < parts) {   // one warp per part: find the byte in which the cumulative count passes the rank
+                uint32_t c[8], sum = 0;
+#pragma unroll
+                for (int b = 0; b < 8; b++) { c[b] = shist[warp][lane * 8 + b]; sum += c[b]; }
+                uint32_t incl = sum;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane >= o) incl += v; }
+                const uint32_t excl = incl - sum, rank = s_rank[warp];
+                if (rank >= excl && rank < incl) {          // exactly one lane
+                    uint32_t acc = excl;
+                    int d = 0;
+                    bool found = false;   // d stops at the first byte whose cumulative count exceeds the rank
+#pragma unroll
+                    for (int b = 0; b < 8; b++) {
+                        if (!found) {
+                            if (rank >= acc + c[b]) { acc += c[b]; d = b + 1; }
+                            else found = true;
+                        }
+                    }
+                    s_prefix[warp] |= (lane * 8u + (uint32_t)d) << shift;
+                    s_rank[warp] = rank - acc;
+                }
+            }
+            __syncthreads();
+        }
+        // stable partition: elements below the median key go low, the first (rank + 1) of the equal ones too
+        uint32_t dest[E];
+#pragma unroll 1
+        for (uint32_t k = 0; k < E; k++) {
+            const uint32_t part = (k * 1024) / S, m = s_prefix[part], need_eq = s_rank[part] + 1u;
+            const bool less = key[k] < m, eq = key[k] == m;
+            const uint32_t bl = __ballot_sync(0xffffffffu, less), be = __ballot_sync(0xffffffffu, eq);
+            if (lane == 0) { s_warp[warp][0] = __popc(bl); s_warp[warp][1] = __popc(be); }
+            __syncthreads();
+            uint32_t less_before = s_carry[part][0] + __popc(bl & ((1u << lane) - 1u));
+            uint32_t eq_before = s_carry[part][1] + __popc(be & ((1u << lane) - 1u));
+            for (uint32_t w = 0; w < warp; w++) { less_before += s_warp[w][0]; eq_before += s_warp[w][1]; }
+            const uint32_t e_local = (k * 1024 + t) - part * S;
+            const uint32_t low_before = less_before + min(eq_before, need_eq);
+            const bool goes_low = less || (eq && eq_before < need_eq);
+            dest[k] = part * S + (goes_low ? low_before : S / 2 + (e_local - low_before));
+            __syncthreads();
+            if (t == 1023) {   // last thread of the slab: its inclusive counts are the slab totals
+                const bool next_same = (k + 1 < E) && ((k + 1) * 1024) / S == part;
+                s_carry[part][0] = next_same ? less_before + (less ? 1u : 0u) : 0u;
+                s_carry[part][1] = next_same ? eq_before + (eq ? 1u : 0u) : 0u;
+            }
+            __syncthreads();
+        }
+        float4 mine[E];
+#pragma unroll
+        for (uint32_t k = 0; k < E; k++) mine[k] = sp[k * 1024 + t];
+        __syncthreads();
+#pragma unroll
+        for (uint32_t k = 0; k < E; k++) sp[dest[k]] = mine[k];
+        __syncthreads();
+    }
+#pragma unroll
+    for (uint32_t k = 0; k < E; k++) gp[k * 1024 + t] = sp[k * 1024 + t];
 }
 
 __global__ void __launch_bounds__(256) inverse_perm_kernel(const float4* __restrict__ pts, const uint32_t* __restrict__ counts,
@@ -545,8 +678,28 @@ int icp_build_cloudset(icpsymm_ctx* ctx, CloudSet& cs, const float* xyz, bool on
                                                    B.vals_b, slots, 0, end_bit, st));
     gather_kernel<<<gb, 256, 0, st>>>(raw, stride_bytes, cs.counts, mc, sh.pitch, ns, B.vals_b, cs.pts);
     {
-        const uint32_t wins = sh.pitch / kKdWindow;     // windows per segment (only full ones are refined)
-        if (wins) kd_refine_kernel<<<ns * wins, kKdWindow / 2, 0, st>>>(cs.pts, cs.counts, sh.pitch, wins);
+        // k-d refinement of the curve order: coarse median partitions of 8192-point windows (the set that is
+        // searched only: they shape the upper levels of its hierarchy; measured on the 1M pair: loop -10 %
+        // for 10 us of build time, while the source gains nothing from them), then the sorting
+        // refinement of every 512-point window (both sets; only full windows are touched)
+#ifndef ICP_KD_COARSE_TGT
+#define ICP_KD_COARSE_TGT 1
+#endif
+#ifndef ICP_KD_COARSE_SRC
+#define ICP_KD_COARSE_SRC 0
+#endif
+        const bool coarse = cs.slot == 1 ? (ICP_KD_COARSE_TGT != 0) : (ICP_KD_COARSE_SRC != 0);
+        if (coarse && sh.pitch >= 8192) {
+            const size_t sm = (size_t)8192 * 20;
+            ICP_CUDA_CHECK(cudaFuncSetAttribute(kd_coarse_kernel<8192>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            kd_coarse_kernel<8192><<<ns * (sh.pitch / 8192), 1024, sm, st>>>(cs.pts, cs.counts, sh.pitch, sh.pitch / 8192);
+        } else if (coarse && sh.pitch >= 4096) {
+            const size_t sm = (size_t)4096 * 20;
+            ICP_CUDA_CHECK(cudaFuncSetAttribute(kd_coarse_kernel<4096>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            kd_coarse_kernel<4096><<<ns * (sh.pitch / 4096), 1024, sm, st>>>(cs.pts, cs.counts, sh.pitch, sh.pitch / 4096);
+        }
+        const uint32_t wins = sh.pitch / 512;
+        if (wins) kd_refine_kernel<512><<<ns * wins, 256, 0, st>>>(cs.pts, cs.counts, sh.pitch, wins);
     }
     inverse_perm_kernel<<<gb, 256, 0, st>>>(cs.pts, cs.counts, sh.pitch, ns, cs.pos_of_orig);
     {
