@@ -276,8 +276,7 @@ __global__ void __launch_bounds__(1024) kd_coarse_kernel(float4* __restrict__ pt
                                                          uint32_t pitch, uint32_t wins_per_seg) {
     constexpr uint32_t E = W / 1024, MAXP = W / (2 * kKdFine);
     extern __shared__ __align__(16) unsigned char kd_smem[];
-    float4* sp = reinterpret_cast<float4*>(kd_smem);
-    uint32_t* skey = reinterpret_cast<uint32_t*>(sp + W);
+    float4* sp = reinterpret_cast<float4*>(kd_smem);     // the window's points; keys live in registers
     __shared__ uint32_t sbox[MAXP][6];
     __shared__ uint32_t shist[MAXP][256];
     __shared__ uint32_t s_prefix[MAXP], s_rank[MAXP];       // radix select state per part
@@ -690,11 +689,11 @@ int icp_build_cloudset(icpsymm_ctx* ctx, CloudSet& cs, const float* xyz, bool on
 #endif
         const bool coarse = cs.slot == 1 ? (ICP_KD_COARSE_TGT != 0) : (ICP_KD_COARSE_SRC != 0);
         if (coarse && sh.pitch >= 8192) {
-            const size_t sm = (size_t)8192 * 20;
+            const size_t sm = (size_t)8192 * sizeof(float4);
             ICP_CUDA_CHECK(cudaFuncSetAttribute(kd_coarse_kernel<8192>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
             kd_coarse_kernel<8192><<<ns * (sh.pitch / 8192), 1024, sm, st>>>(cs.pts, cs.counts, sh.pitch, sh.pitch / 8192);
         } else if (coarse && sh.pitch >= 4096) {
-            const size_t sm = (size_t)4096 * 20;
+            const size_t sm = (size_t)4096 * sizeof(float4);
             ICP_CUDA_CHECK(cudaFuncSetAttribute(kd_coarse_kernel<4096>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
             kd_coarse_kernel<4096><<<ns * (sh.pitch / 4096), 1024, sm, st>>>(cs.pts, cs.counts, sh.pitch, sh.pitch / 4096);
         }
