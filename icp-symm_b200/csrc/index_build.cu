@@ -280,7 +280,8 @@ __global__ void __launch_bounds__(1024) kd_coarse_kernel(float4* __restrict__ pt
     __shared__ uint32_t sbox[MAXP][6];
     __shared__ uint32_t shist[MAXP][256];
     __shared__ uint32_t s_prefix[MAXP], s_rank[MAXP];       // radix select state per part
-    __shared__ uint32_t s_warp[32][2], s_carry[MAXP][2];    // partition scan: per-warp counts, running counts per part
+    __shared__ uint32_t s_klo[MAXP], s_khi[MAXP];           // smallest and largest key of the part
+    __shared__ uint32_t s_cnt[E][32][2];                    // partition scan: (less, equal) counts per slab and warp, then their exclusive prefix
     const uint32_t seg = blockIdx.x / wins_per_seg, win = blockIdx.x - seg * wins_per_seg;
     const uint32_t base = win * W;
     if (base + W > counts[seg]) return;                      // partial window: left to the curve order + fine refinement
@@ -289,16 +290,17 @@ __global__ void __launch_bounds__(1024) kd_coarse_kernel(float4* __restrict__ pt
 #pragma unroll
     for (uint32_t k = 0; k < E; k++) sp[k * 1024 + t] = gp[k * 1024 + t];
     __syncthreads();
-    for (uint32_t S = W; S > kKdFine; S >>= 1) {
+    for (uint32_t S = W, logS = 31 - __clz((int)W); S > kKdFine; S >>= 1, logS--) {
         const uint32_t parts = W / S;
         for (uint32_t v = t; v < parts * 6; v += 1024) sbox[v / 6][v % 6] = (v % 6 < 3) ? 0xffffffffu : 0u;
-        if (t < parts) { s_prefix[t] = 0u; s_rank[t] = S / 2 - 1; s_carry[t][0] = 0u; s_carry[t][1] = 0u; }
+        if (t < parts) { s_prefix[t] = 0u; s_rank[t] = S / 2 - 1; }
+        if (S == W) for (uint32_t v = t; v < MAXP * 256; v += 1024) shist[v >> 8][v & 255] = 0u;
         __syncthreads();
         // bounding box of every part
 #pragma unroll
         for (uint32_t k = 0; k < E; k++) {
             const float4 p = sp[k * 1024 + t];
-            const uint32_t part = (k * 1024) / S;
+            const uint32_t part = (k << 10) >> logS;
             const uint32_t ox = float_to_ordered(p.x), oy = float_to_ordered(p.y), oz = float_to_ordered(p.z);
             const uint32_t lx = __reduce_min_sync(0xffffffffu, ox), hx = __reduce_max_sync(0xffffffffu, ox);
             const uint32_t ly = __reduce_min_sync(0xffffffffu, oy), hy = __reduce_max_sync(0xffffffffu, oy);
@@ -311,75 +313,126 @@ __global__ void __launch_bounds__(1024) kd_coarse_kernel(float4* __restrict__ pt
         }
         __syncthreads();
         // keys: the coordinate along the longest axis of the part
+        if (t < parts) {
+            const float ex = ordered_to_float(sbox[t][3]) - ordered_to_float(sbox[t][0]);
+            const float ey = ordered_to_float(sbox[t][4]) - ordered_to_float(sbox[t][1]);
+            const float ez = ordered_to_float(sbox[t][5]) - ordered_to_float(sbox[t][2]);
+            const int ax = (ex >= ey && ex >= ez) ? 0 : (ey >= ez ? 1 : 2);
+            s_klo[t] = sbox[t][ax]; s_khi[t] = sbox[t][3 + ax];    // float_to_ordered is monotone: these are the extreme keys
+        }
         uint32_t key[E];
 #pragma unroll
         for (uint32_t k = 0; k < E; k++) {
-            const uint32_t part = (k * 1024) / S;
+            const uint32_t part = (k << 10) >> logS;
             const float ex = ordered_to_float(sbox[part][3]) - ordered_to_float(sbox[part][0]);
             const float ey = ordered_to_float(sbox[part][4]) - ordered_to_float(sbox[part][1]);
             const float ez = ordered_to_float(sbox[part][5]) - ordered_to_float(sbox[part][2]);
             const float4 p = sp[k * 1024 + t];
             key[k] = float_to_ordered((ex >= ey && ex >= ez) ? p.x : (ey >= ez ? p.y : p.z));
         }
-        // exact median key of every part: radix select, most significant byte first
-        for (int shift = 24; shift >= 0; shift -= 8) {
-            for (uint32_t v = t; v < parts * 256; v += 1024) shist[v >> 8][v & 255] = 0u;
-            __syncthreads();
-            const uint32_t mask = (shift == 24) ? 0u : (0xffffffffu << (shift + 8));
+        __syncthreads();   // s_klo / s_khi
+        // exact median key of every part: radix select, most significant digit first, on (key - smallest key
+        // of the part).  Starting at the top bit of the part's key RANGE spreads the first histogram over all
+        // of its 256 bins; the raw high bytes of neighbouring coordinates are nearly all equal and would
+        // serialise thousands of shared-memory atomics on a handful of bins.
+        int nbits[E];   // width of the part's key range
+#pragma unroll
+        for (uint32_t k = 0; k < E; k++) {
+            const uint32_t part = (k << 10) >> logS;
+            key[k] -= s_klo[part];
+            nbits[k] = 32 - __clz((int)(s_khi[part] - s_klo[part]));
+        }
+        for (int r = 0; r < 4; r++) {   // (the histograms are zero here: cleared below by their readers)
 #pragma unroll
             for (uint32_t k = 0; k < E; k++) {
-                const uint32_t part = (k * 1024) / S;
-                if ((key[k] & mask) == s_prefix[part]) atomicAdd(&shist[part][(key[k] >> shift) & 255u], 1u);
+                const uint32_t part = (k << 10) >> logS;
+                const int remaining = nbits[k] - 8 * r;   // key bits not yet fixed
+                if (remaining > 0) {
+                    const int w = remaining < 8 ? remaining : 8, shift = remaining - w;
+                    const bool in = remaining >= 32 || (key[k] >> remaining) == (s_prefix[part] >> remaining);
+                    if (in) atomicAdd(&shist[part][(key[k] >> shift) & ((1u << w) - 1u)], 1u);
+                }
             }
             __syncthreads();
-            if (warp < parts) {   // one warp per part: find the byte in which the cumulative count passes the rank
-                uint32_t c[8], sum = 0;
+            if (warp < parts) {   // one warp per part: find the digit in which the cumulative count passes the rank
+                const int remaining = (32 - __clz((int)(s_khi[warp] - s_klo[warp]))) - 8 * r;
+                if (remaining > 0) {
+                    const int w = remaining < 8 ? remaining : 8, shift = remaining - w;
+                    uint32_t c[8], sum = 0;
 #pragma unroll
-                for (int b = 0; b < 8; b++) { c[b] = shist[warp][lane * 8 + b]; sum += c[b]; }
-                uint32_t incl = sum;
+                    for (int b = 0; b < 8; b++) { c[b] = shist[warp][lane * 8 + b]; sum += c[b]; shist[warp][lane * 8 + b] = 0u; }
+                    uint32_t incl = sum;
 #pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane >= o) incl += v; }
-                const uint32_t excl = incl - sum, rank = s_rank[warp];
-                if (rank >= excl && rank < incl) {          // exactly one lane
-                    uint32_t acc = excl;
-                    int d = 0;
-                    bool found = false;   // d stops at the first byte whose cumulative count exceeds the rank
+                    for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane >= o) incl += v; }
+                    const uint32_t excl = incl - sum, rank = s_rank[warp];
+                    if (rank >= excl && rank < incl) {          // exactly one lane
+                        uint32_t acc = excl;
+                        int d = 0;
+                        bool found = false;   // d stops at the first digit whose cumulative count exceeds the rank
 #pragma unroll
-                    for (int b = 0; b < 8; b++) {
-                        if (!found) {
-                            if (rank >= acc + c[b]) { acc += c[b]; d = b + 1; }
-                            else found = true;
+                        for (int b = 0; b < 8; b++) {
+                            if (!found) {
+                                if (rank >= acc + c[b]) { acc += c[b]; d = b + 1; }
+                                else found = true;
+                            }
                         }
+                        s_prefix[warp] |= (lane * 8u + (uint32_t)d) << shift;
+                        s_rank[warp] = rank - acc;
                     }
-                    s_prefix[warp] |= (lane * 8u + (uint32_t)d) << shift;
-                    s_rank[warp] = rank - acc;
                 }
             }
             __syncthreads();
         }
-        // stable partition: elements below the median key go low, the first (rank + 1) of the equal ones too
-        uint32_t dest[E];
-#pragma unroll 1
+        // stable partition: elements below the median key go low, the first (rank + 1) of the equal ones too.
+        // Counts of (less, equal) per warp and slab k -> one exclusive scan over the E x 32 (slab, warp) cells in
+        // element order, restarted at every part boundary, done by warp 0.
+        uint32_t bl[E], be[E];
+#pragma unroll
         for (uint32_t k = 0; k < E; k++) {
-            const uint32_t part = (k * 1024) / S, m = s_prefix[part], need_eq = s_rank[part] + 1u;
+            const uint32_t m = s_prefix[(k << 10) >> logS];
+            bl[k] = __ballot_sync(0xffffffffu, key[k] < m);
+            be[k] = __ballot_sync(0xffffffffu, key[k] == m);
+            if (lane == 0) { s_cnt[k][warp][0] = __popc(bl[k]); s_cnt[k][warp][1] = __popc(be[k]); }
+        }
+        __syncthreads();
+        if (warp == 0) {
+            // element order is slab-major: cell (k, w) precedes (k, w+1) and (k+1, 0); lane l takes the E
+            // consecutive cells l*E .. l*E+E-1
+            uint32_t cl[E], ce[E], suml = 0, sume = 0;
+#pragma unroll
+            for (uint32_t c = 0; c < E; c++) {
+                const uint32_t cell = lane * E + c, k = cell >> 5, w = cell & 31u;
+                cl[c] = s_cnt[k][w][0]; ce[c] = s_cnt[k][w][1];
+                suml += cl[c]; sume += ce[c];
+            }
+            uint32_t il = suml, ie = sume;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t vl = __shfl_up_sync(0xffffffffu, il, o), ve = __shfl_up_sync(0xffffffffu, ie, o);
+                if ((int)lane >= o) { il += vl; ie += ve; }
+            }
+            uint32_t al = il - suml, ae = ie - sume;     // exclusive over the whole window, element order
+#pragma unroll
+            for (uint32_t c = 0; c < E; c++) {
+                const uint32_t cell = lane * E + c, k = cell >> 5, w = cell & 31u;
+                s_cnt[k][w][0] = al; s_cnt[k][w][1] = ae;
+                al += cl[c]; ae += ce[c];
+            }
+        }
+        __syncthreads();
+        uint32_t dest[E];
+#pragma unroll
+        for (uint32_t k = 0; k < E; k++) {
+            const uint32_t part = (k << 10) >> logS, m = s_prefix[part], need_eq = s_rank[part] + 1u;
+            // window-wide exclusive counts minus those at the start of the part = counts inside the part
+            const uint32_t k0 = (part * S) >> 10;
+            const uint32_t less_before = s_cnt[k][warp][0] - s_cnt[k0][0][0] + __popc(bl[k] & ((1u << lane) - 1u));
+            const uint32_t eq_before = s_cnt[k][warp][1] - s_cnt[k0][0][1] + __popc(be[k] & ((1u << lane) - 1u));
             const bool less = key[k] < m, eq = key[k] == m;
-            const uint32_t bl = __ballot_sync(0xffffffffu, less), be = __ballot_sync(0xffffffffu, eq);
-            if (lane == 0) { s_warp[warp][0] = __popc(bl); s_warp[warp][1] = __popc(be); }
-            __syncthreads();
-            uint32_t less_before = s_carry[part][0] + __popc(bl & ((1u << lane) - 1u));
-            uint32_t eq_before = s_carry[part][1] + __popc(be & ((1u << lane) - 1u));
-            for (uint32_t w = 0; w < warp; w++) { less_before += s_warp[w][0]; eq_before += s_warp[w][1]; }
             const uint32_t e_local = (k * 1024 + t) - part * S;
             const uint32_t low_before = less_before + min(eq_before, need_eq);
             const bool goes_low = less || (eq && eq_before < need_eq);
             dest[k] = part * S + (goes_low ? low_before : S / 2 + (e_local - low_before));
-            __syncthreads();
-            if (t == 1023) {   // last thread of the slab: its inclusive counts are the slab totals
-                const bool next_same = (k + 1 < E) && ((k + 1) * 1024) / S == part;
-                s_carry[part][0] = next_same ? less_before + (less ? 1u : 0u) : 0u;
-                s_carry[part][1] = next_same ? eq_before + (eq ? 1u : 0u) : 0u;
-            }
-            __syncthreads();
         }
         float4 mine[E];
 #pragma unroll
