@@ -732,7 +732,7 @@ int icp_build_cloudset(icpsymm_ctx* ctx, CloudSet& cs, const float* xyz, bool on
     {
         // k-d refinement of the curve order: coarse median partitions of 8192-point windows (the set that is
         // searched only: they shape the upper levels of its hierarchy; measured on the 1M pair: loop -10 %
-        // for 10 us of build time, while the source gains nothing from them), then the sorting
+        // for 60 us of build time, while the source gains nothing from them), then the sorting
         // refinement of every 512-point window (both sets; only full windows are touched)
 #ifndef ICP_KD_COARSE_TGT
 #define ICP_KD_COARSE_TGT 1
