@@ -4,6 +4,8 @@ Bars (BASELINE.json north_star): nearest-neighbour indices bit-exact (ties -> lo
 fp32 squared distances bit-exact, final transform rotation <= 1e-5 rad, translation <= 1e-5 x
 cloud extent, RMSE relative <= 1e-5.
 """
+import zlib
+
 import numpy as np
 import pytest
 
@@ -529,6 +531,41 @@ def test_nn_degenerate_distributions(ctx, case):
     assert np.isfinite(ctx.get_normals(0)).all() and np.isfinite(ctx.get_normals(1)).all()
     T, st, rc = ctx.register_symm(3, 0.0)
     assert np.isfinite(T).all() and np.isfinite(st["diff"])
+
+
+@pytest.mark.parametrize("case", ["signs", "duplicates", "lattice", "huge_range", "tiny", "constant_axis", "two_values"])
+def test_nn_large_targets_with_awkward_coordinates(ctx, case):
+    """targets above 8192 points go through the coarse k-d partition (radix-select medians, stable
+    partition): whatever the key distribution, it must only permute the points -- searches stay bit-exact,
+    every original index is returned by some query when the queries are the targets themselves"""
+    rng = np.random.default_rng(zlib.crc32(case.encode()))
+    m, n = 3 * 8192 + 777, 3000
+    if case == "signs":                 # coordinates on both sides of zero: ordered keys span more than 2^31
+        tgt = rng.uniform(-3, 3, (m, 3))
+    elif case == "duplicates":          # 64 distinct positions only: every median is a tie
+        tgt = rng.integers(0, 4, (m, 3)).astype(np.float64)
+    elif case == "lattice":
+        g = np.stack(np.meshgrid(np.arange(30), np.arange(30), np.arange(30), indexing="ij"), -1).reshape(-1, 3)
+        tgt = g[rng.permutation(len(g))[:m]] * 0.5
+    elif case == "huge_range":          # exponents from 1e-20 to 1e+18 with both signs
+        tgt = rng.standard_normal((m, 3)) * 10.0 ** rng.uniform(-20, 18, (m, 1))
+    elif case == "tiny":
+        tgt = rng.standard_normal((m, 3)) * 1e-30
+    elif case == "constant_axis":       # zero extent along two axes
+        tgt = np.c_[rng.standard_normal(m), np.full(m, 7.25), np.zeros(m)]
+    else:                               # each coordinate takes two values: 8 distinct points
+        tgt = rng.integers(0, 2, (m, 3)) * 1e3 - 500.0
+    tgt = tgt.astype(np.float32)
+    q = (tgt[rng.integers(0, m, n)] * rng.uniform(0.9, 1.1, (n, 1)) + rng.standard_normal((n, 3)) * 1e-3 * (np.abs(tgt).max() if case != "huge_range" else 1.0)).astype(np.float32)
+    _check_nn(ctx, q, tgt)
+    # the targets as queries: with distinct points every index comes back as its own neighbour
+    if case == "signs":
+        ctx.set_source(tgt)
+        idx, d2 = ctx.find_correspondences()
+        assert np.array_equal(idx, np.arange(m)) and not d2.any()
+    if case != "huge_range":            # (squared distances across 38 decades overflow fp32: searches stay exact, moments do not)
+        ctx.estimate_normals(10)
+        assert np.isfinite(ctx.get_normals(1)).all()
 
 
 def test_normals_knn_ties_by_lowest_index(ctx):
