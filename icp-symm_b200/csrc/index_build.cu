@@ -168,11 +168,20 @@ __global__ void __launch_bounds__(kKdWindow / 2) kd_refine_kernel(float4* __rest
                                                                  uint32_t pitch, uint32_t wins_per_seg) {
     constexpr uint32_t kKdHalf = kKdWindow / 2, kKdIdxMask = kKdWindow - 1;
     __shared__ float4 sp[kKdWindow];
-    __shared__ uint32_t skey[kKdWindow];             // ordered coordinate, low 9 bits replaced by the element index
-    __shared__ uint32_t sbox[kKdWindow / ICP_LEAF][6];                 // per part: ordered-uint lo xyz, hi xyz
+    __shared__ __align__(16) uint32_t skey[kKdWindow];             // ordered coordinate, low 9 bits replaced by the element index
+    __shared__ __align__(16) uint32_t sbox[kKdWindow / ICP_LEAF][6];                 // per part: ordered-uint lo xyz, hi xyz
+    // split levels with parts of 64 points or more only PARTITION at the median (radix select + stable
+    // partition, as in kd_coarse_kernel below); the sort is kept for the last three levels (32, 16 -> 8)
+    // (explicit alignment: without it ptxas merged neighbouring 4-byte shared accesses into misaligned 8-byte ones)
+    constexpr uint32_t kMaxParts = kKdWindow / 64, kCells = kKdWindow / 32, kCellsPerLane = kCells >= 32 ? kCells / 32 : 1;
+    static_assert(kKdWindow <= 1024, "histograms of larger windows do not fit the static shared memory");
+    __shared__ __align__(16) uint32_t shist[kMaxParts][256];
+    __shared__ __align__(16) uint32_t s_prefix[kMaxParts], s_rank[kMaxParts], s_klo[kMaxParts], s_khi[kMaxParts], s_axis[kMaxParts];
+    __shared__ __align__(16) uint32_t s_cnt[kCells][2];
     const uint32_t seg = blockIdx.x / wins_per_seg, win = blockIdx.x - seg * wins_per_seg;
     const uint32_t base = win * kKdWindow;
     if (base + kKdWindow > counts[seg]) return;      // partial window (or padding): keep the curve order
+    for (uint32_t v = threadIdx.x; v < kMaxParts * 256; v += kKdHalf) shist[v >> 8][v & 255] = 0u;
     float4* gp = pts + (size_t)seg * pitch + base;
     const uint32_t t = threadIdx.x;                  // kKdHalf threads, elements t and t + kKdHalf
     sp[t] = gp[t];
@@ -205,6 +214,125 @@ __global__ void __launch_bounds__(kKdWindow / 2) kd_refine_kernel(float4* __rest
             }
         }
         __syncthreads();
+        if (S >= 64) {
+            const uint32_t lane = t & 31, warp = t >> 5;
+            if (t < parts) {
+                const float ex = ordered_to_float(sbox[t][3]) - ordered_to_float(sbox[t][0]);
+                const float ey = ordered_to_float(sbox[t][4]) - ordered_to_float(sbox[t][1]);
+                const float ez = ordered_to_float(sbox[t][5]) - ordered_to_float(sbox[t][2]);
+                const uint32_t ax = (ex >= ey && ex >= ez) ? 0u : (ey >= ez ? 1u : 2u);
+                s_axis[t] = ax; s_klo[t] = sbox[t][ax]; s_khi[t] = sbox[t][3 + ax];
+                s_prefix[t] = 0u; s_rank[t] = S / 2 - 1;
+            }
+            __syncthreads();
+            uint32_t key[2], prt[2];
+            int nbits[2];
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const uint32_t e = t + kKdHalf * h;
+                prt[h] = e / S;
+                const float4 p = sp[e];
+                const uint32_t ax = s_axis[prt[h]];
+                key[h] = float_to_ordered(ax == 0u ? p.x : (ax == 1u ? p.y : p.z)) - s_klo[prt[h]];
+                nbits[h] = 32 - __clz((int)(s_khi[prt[h]] - s_klo[prt[h]]));
+            }
+            for (int r = 0; r < 4; r++) {   // radix select of the median key, on the part's key range (see kd_coarse_kernel)
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const int remaining = nbits[h] - 8 * r;
+                    if (remaining > 0) {
+                        const int w = remaining < 8 ? remaining : 8, shift = remaining - w;
+                        const bool in = remaining >= 32 || (key[h] >> remaining) == (s_prefix[prt[h]] >> remaining);
+                        if (in) atomicAdd(&shist[prt[h]][(key[h] >> shift) & ((1u << w) - 1u)], 1u);
+                    }
+                }
+                __syncthreads();
+                if (warp < parts) {
+                    const int remaining = (32 - __clz((int)(s_khi[warp] - s_klo[warp]))) - 8 * r;
+                    if (remaining > 0) {
+                        const int w = remaining < 8 ? remaining : 8, shift = remaining - w;
+                        uint32_t c[8], sum = 0;
+#pragma unroll
+                        for (int b = 0; b < 8; b++) { c[b] = shist[warp][lane * 8 + b]; sum += c[b]; shist[warp][lane * 8 + b] = 0u; }
+                        uint32_t incl = sum;
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane >= o) incl += v; }
+                        const uint32_t excl = incl - sum, rank = s_rank[warp];
+                        if (rank >= excl && rank < incl) {
+                            uint32_t acc = excl;
+                            int d = 0;
+                            bool found = false;
+#pragma unroll
+                            for (int b = 0; b < 8; b++) {
+                                if (!found) {
+                                    if (rank >= acc + c[b]) { acc += c[b]; d = b + 1; }
+                                    else found = true;
+                                }
+                            }
+                            s_prefix[warp] |= (lane * 8u + (uint32_t)d) << shift;
+                            s_rank[warp] = rank - acc;
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+            // stable partition (ties at the median go low in the current order)
+            uint32_t bl[2], be[2];
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const uint32_t m = s_prefix[prt[h]];
+                bl[h] = __ballot_sync(0xffffffffu, key[h] < m);
+                be[h] = __ballot_sync(0xffffffffu, key[h] == m);
+                if (lane == 0) { const uint32_t cell = (t + kKdHalf * h) >> 5; s_cnt[cell][0] = __popc(bl[h]); s_cnt[cell][1] = __popc(be[h]); }
+            }
+            __syncthreads();
+            if (warp == 0) {
+                uint32_t cl[kCellsPerLane], ce[kCellsPerLane], suml = 0, sume = 0;
+#pragma unroll
+                for (uint32_t c = 0; c < kCellsPerLane; c++) {
+                    const uint32_t cell = lane * kCellsPerLane + c;
+                    cl[c] = cell < kCells ? s_cnt[cell][0] : 0u; ce[c] = cell < kCells ? s_cnt[cell][1] : 0u;
+                    suml += cl[c]; sume += ce[c];
+                }
+                uint32_t il = suml, ie = sume;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t vl = __shfl_up_sync(0xffffffffu, il, o), ve = __shfl_up_sync(0xffffffffu, ie, o);
+                    if ((int)lane >= o) { il += vl; ie += ve; }
+                }
+                uint32_t al = il - suml, ae = ie - sume;
+#pragma unroll
+                for (uint32_t c = 0; c < kCellsPerLane; c++) {
+                    const uint32_t cell = lane * kCellsPerLane + c;
+                    if (cell < kCells) { s_cnt[cell][0] = al; s_cnt[cell][1] = ae; }
+                    al += cl[c]; ae += ce[c];
+                }
+            }
+            __syncthreads();
+            uint32_t dest[2];
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const uint32_t e = t + kKdHalf * h, cell = e >> 5, cell0 = (prt[h] * S) >> 5;
+                const uint32_t m = s_prefix[prt[h]], need_eq = s_rank[prt[h]] + 1u;
+                const uint32_t less_before = s_cnt[cell][0] - s_cnt[cell0][0] + __popc(bl[h] & ((1u << lane) - 1u));
+                const uint32_t eq_before = s_cnt[cell][1] - s_cnt[cell0][1] + __popc(be[h] & ((1u << lane) - 1u));
+                const bool less = key[h] < m, eq = key[h] == m;
+                const uint32_t low_before = less_before + min(eq_before, need_eq);
+                const bool goes_low = less || (eq && eq_before < need_eq);
+                dest[h] = prt[h] * S + (goes_low ? low_before : S / 2 + ((e - prt[h] * S) - low_before));
+#ifdef ICP_DEBUG_ASSERT
+                if (dest[h] >= kKdWindow || (goes_low && low_before >= S / 2))
+                    printf("kd_refine S=%u e=%u part=%u m=%u key=%u need_eq=%u less_before=%u eq_before=%u cell=%u cell0=%u cnt=%u,%u cnt0=%u,%u nbits=%d\n", S, e, prt[h], m, key[h], need_eq, less_before, eq_before, cell, cell0, s_cnt[cell][0], s_cnt[cell][1], s_cnt[cell0][0], s_cnt[cell0][1], nbits[h]);
+                dest[h] &= kKdIdxMask;
+#endif
+            }
+            const float4 a = sp[t], b = sp[t + kKdHalf];
+            __syncthreads();
+            sp[dest[0]] = a;
+            sp[dest[1]] = b;
+            __syncthreads();
+            continue;
+        }
 #pragma unroll
         for (int h = 0; h < 2; h++) {
             const uint32_t e = t + kKdHalf * h, part = e / S;
@@ -277,11 +405,11 @@ __global__ void __launch_bounds__(1024) kd_coarse_kernel(float4* __restrict__ pt
     constexpr uint32_t E = W / 1024, MAXP = W / (2 * kKdFine);
     extern __shared__ __align__(16) unsigned char kd_smem[];
     float4* sp = reinterpret_cast<float4*>(kd_smem);     // the window's points; keys live in registers
-    __shared__ uint32_t sbox[MAXP][6];
-    __shared__ uint32_t shist[MAXP][256];
-    __shared__ uint32_t s_prefix[MAXP], s_rank[MAXP];       // radix select state per part
-    __shared__ uint32_t s_klo[MAXP], s_khi[MAXP];           // smallest and largest key of the part
-    __shared__ uint32_t s_cnt[E][32][2];                    // partition scan: (less, equal) counts per slab and warp, then their exclusive prefix
+    __shared__ __align__(16) uint32_t sbox[MAXP][6];
+    __shared__ __align__(16) uint32_t shist[MAXP][256];
+    __shared__ __align__(16) uint32_t s_prefix[MAXP], s_rank[MAXP];       // radix select state per part
+    __shared__ __align__(16) uint32_t s_klo[MAXP], s_khi[MAXP];           // smallest and largest key of the part
+    __shared__ __align__(16) uint32_t s_cnt[E][32][2];                    // partition scan: (less, equal) counts per slab and warp, then their exclusive prefix
     const uint32_t seg = blockIdx.x / wins_per_seg, win = blockIdx.x - seg * wins_per_seg;
     const uint32_t base = win * W;
     if (base + W > counts[seg]) return;                      // partial window: left to the curve order + fine refinement
