@@ -4,10 +4,11 @@
 // construction hidden inside pcl::search::KdTree (ICP/myicp.cpp:158-159).  One-off per cloud;
 // the hot loop only reads the result.  Steps, all on the context stream:
 //   bbox reduce -> 30-bit Hilbert key per point (uniform cell size) -> radix sort (CUB, keys are
-//   segment<<32 | key so a whole batch sorts in one pass) -> gather into the float4 layout
-//   with the original index in .w -> local k-d refinement of every 512-point window -> inverse
-//   permutation -> tight leaf boxes written into their parents' wide-node
-//   records -> one kernel per upper level (union of a node's 8 children into its parent's record).
+//   segment<<30 | key so a whole batch sorts in one pass) -> gather into the float4 layout
+//   with the original index in .w -> k-d partition of every 8192-point window (searched set only)
+//   -> k-d refinement of every 512-point window -> inverse permutation -> split-unit masks ->
+//   tight leaf boxes written into their parents' wide-node records -> one kernel per upper level
+//   (union of a node's 8 children into its parent's record).
 #include <cfloat>
 #include <cstring>
 #include <cub/device/device_radix_sort.cuh>
@@ -346,9 +347,9 @@ __global__ void __launch_bounds__(kKdWindow / 2) kd_refine_kernel(float4* __rest
         }
         __syncthreads();
         // bitonic sort inside every part (parts are aligned powers of two; keys are unique).  Thread t
-        // keeps the keys of elements t and t+256 in registers: partners at distance 256 are the
-        // thread's own pair, distances below 32 are exchanged with warp shuffles, only distances
-        // 32..128 go through shared memory (19 of the 155 steps of all six levels)
+        // keeps the keys of elements t and t + kKdHalf in registers; with parts of 32 and 16 points (the
+        // only ones that are still sorted) every exchange is a warp shuffle.  The general form below
+        // also handles larger parts: the thread's own pair at distance kKdHalf, shared memory from 32 up.
         uint32_t v0 = skey[t], v1 = skey[t + kKdHalf];
         for (uint32_t k = 2; k <= S; k <<= 1) {
             for (uint32_t j = k >> 1; j > 0; j >>= 1) {
