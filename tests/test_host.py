@@ -37,6 +37,18 @@ def test_header_cites_the_reference_interfaces():
         assert cite in hdr
 
 
+def test_python_binding_constants_match_the_header():
+    """option keys and status codes of the ctypes binding are the ones include/icpsymm.h declares"""
+    import re
+    import icpsymm as icp
+    hdr = open(os.path.join(ROOT, "include", "icpsymm.h")).read()
+    enums = dict((m.group(1), int(m.group(2))) for m in re.finditer(r"\b(ICPSYMM_[A-Z0-9_]+)\s*=\s*(-?\d+)", hdr))
+    opts = {k: v for k, v in enums.items() if k.startswith("ICPSYMM_OPT_")}
+    assert len(opts) >= 10
+    for name, value in opts.items():
+        assert getattr(icp, name[len("ICPSYMM_"):]) == value, name
+
+
 def test_status_strings_and_struct_layout(built):
     import icpsymm
     lib = icpsymm.load()
