@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(kNNThreads, 4) nn_accum_kernel(const __grid_co
             }
         }
         // warp-synchronous exact search: the 32 lanes are 32 neighbouring source points
-        // (split units, see unit_split_kernel, are not walked per cluster here: wrapping this walk in a
+        // (split units, see finish_units_kernel in index_build.cu, are not walked per cluster here: wrapping this walk in a
         // pass loop costs the common case 15 %, far more than the rare split unit costs)
         if (!lp.identity_pairs && nt > 0) nn_traverse_warp(P.tgt.shape, tbox, tpts, p.x, p.y, p.z, active, 0u, b);
         float v[40];   // declared after the walk so that none of it is live across it; ICP_NSUMS = 37 used

@@ -575,15 +575,6 @@ __global__ void __launch_bounds__(1024) kd_coarse_kernel(float4* __restrict__ pt
     for (uint32_t k = 0; k < E; k++) gp[k * 1024 + t] = sp[k * 1024 + t];
 }
 
-__global__ void __launch_bounds__(256) inverse_perm_kernel(const float4* __restrict__ pts, const uint32_t* __restrict__ counts,
-                                                           uint32_t pitch, uint32_t nseg, uint32_t* __restrict__ pos_of_orig) {
-    size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= (size_t)nseg * pitch) return;
-    const uint32_t seg = (uint32_t)(j / pitch), i = (uint32_t)(j - (size_t)seg * pitch);
-    if (i >= counts[seg]) return;
-    pos_of_orig[(size_t)seg * pitch + __float_as_uint(pts[j].w)] = i;
-}
-
 // ---- split units ------------------------------------------------------------------------------
 // A unit is 32 consecutive sorted points: the 32 queries one warp searches together.  The curve leaves
 // and re-enters a surface, so about one unit in a hundred holds two clusters that lie far apart; its
@@ -595,68 +586,9 @@ __global__ void __launch_bounds__(256) inverse_perm_kernel(const float4* __restr
 #ifndef ICP_SPLIT_RATIO2
 #define ICP_SPLIT_RATIO2 6.f    // (unit width / group width)^2 from which a unit counts as two clusters (swept: 4..9 equal, 2 and 16 worse)
 #endif
-__global__ void __launch_bounds__(256) unit_split_kernel(const float4* __restrict__ pts, const uint32_t* __restrict__ counts,
-                                                         uint32_t pitch, uint32_t units_per_seg, uint32_t nseg,
-                                                         uint32_t* __restrict__ unit_split) {
-    const size_t wid = ((size_t)blockIdx.x * 256 + threadIdx.x) >> 5;
-    const uint32_t lane = threadIdx.x & 31;
-    if (wid >= (size_t)nseg * units_per_seg) return;
-    const uint32_t seg = (uint32_t)(wid / units_per_seg), unit = (uint32_t)(wid - (size_t)seg * units_per_seg);
-    const uint32_t i = unit * 32u + lane;
-    const bool act = i < counts[seg] && i < pitch;
-    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (act) p = pts[(size_t)seg * pitch + i];
-    const uint32_t none_lo = 0xffffffffu, none_hi = 0u;
-    uint32_t ox = float_to_ordered(p.x), oy = float_to_ordered(p.y), oz = float_to_ordered(p.z);
-    const float lx = ordered_to_float(__reduce_min_sync(0xffffffffu, act ? ox : none_lo)), hx = ordered_to_float(__reduce_max_sync(0xffffffffu, act ? ox : none_hi));
-    const float ly = ordered_to_float(__reduce_min_sync(0xffffffffu, act ? oy : none_lo)), hy = ordered_to_float(__reduce_max_sync(0xffffffffu, act ? oy : none_hi));
-    const float lz = ordered_to_float(__reduce_min_sync(0xffffffffu, act ? oz : none_lo)), hz = ordered_to_float(__reduce_max_sync(0xffffffffu, act ? oz : none_hi));
-    uint32_t mask = 0u;
-    if (__popc(__ballot_sync(0xffffffffu, act)) >= 2) {
-        const float ex = hx - lx, ey = hy - ly, ez = hz - lz;
-        const float c = (ex >= ey && ex >= ez) ? p.x : (ey >= ez ? p.y : p.z);
-        const float mid = (ex >= ey && ex >= ez) ? 0.5f * (lx + hx) : (ey >= ez ? 0.5f * (ly + hy) : 0.5f * (lz + hz));
-        const bool g1 = act && c > mid, g0 = act && !g1;
-        float d2[2];
-#pragma unroll
-        for (int g = 0; g < 2; g++) {
-            const bool in = g ? g1 : g0;
-            const float ax = ordered_to_float(__reduce_max_sync(0xffffffffu, in ? ox : none_hi)) - ordered_to_float(__reduce_min_sync(0xffffffffu, in ? ox : none_lo));
-            const float ay = ordered_to_float(__reduce_max_sync(0xffffffffu, in ? oy : none_hi)) - ordered_to_float(__reduce_min_sync(0xffffffffu, in ? oy : none_lo));
-            const float az = ordered_to_float(__reduce_max_sync(0xffffffffu, in ? oz : none_hi)) - ordered_to_float(__reduce_min_sync(0xffffffffu, in ? oz : none_lo));
-            d2[g] = ax * ax + ay * ay + az * az;   // an empty group gives +inf - -inf... guarded below
-        }
-        const uint32_t m1 = __ballot_sync(0xffffffffu, g1), m0 = __ballot_sync(0xffffffffu, g0);
-        const float whole = ex * ex + ey * ey + ez * ez;
-        if (m0 && m1 && fmaxf(d2[0], d2[1]) * ICP_SPLIT_RATIO2 < whole) mask = m1;
-    }
-    if (lane == 0) unit_split[(size_t)seg * units_per_seg + unit] = mask;
-}
-
 __device__ __forceinline__ void store_child_box(WideNode* __restrict__ rec, uint32_t slot, float3 lo, float3 hi) {
     rec->lox[slot] = lo.x; rec->loy[slot] = lo.y; rec->loz[slot] = lo.z;
     rec->hix[slot] = hi.x; rec->hiy[slot] = hi.y; rec->hiz[slot] = hi.z;
-}
-
-// level 0: one thread per real leaf group; its tight box goes into slot g&7 of record (1, g>>3)
-__global__ void __launch_bounds__(256) leaf_box_kernel(const float4* __restrict__ pts, WideNode* __restrict__ nodes,
-                                                       TreeShape sh, uint32_t nseg) {
-    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t n0 = sh.pitch / ICP_LEAF;
-    if (t >= (size_t)nseg * n0) return;
-    uint32_t seg = (uint32_t)(t / n0), g = (uint32_t)(t - (size_t)seg * n0);
-    const float inf = __int_as_float(0x7f800000);
-    float3 lo = make_float3(inf, inf, inf), hi = make_float3(-inf, -inf, -inf);
-    const float4* lp = pts + (size_t)seg * sh.pitch + (size_t)g * ICP_LEAF;
-#pragma unroll
-    for (int j = 0; j < ICP_LEAF; j++) {
-        float4 c = lp[j];
-        if (__float_as_uint(c.w) != (uint32_t)ICP_INVALID_ID) {
-            lo.x = fminf(lo.x, c.x); lo.y = fminf(lo.y, c.y); lo.z = fminf(lo.z, c.z);
-            hi.x = fmaxf(hi.x, c.x); hi.y = fmaxf(hi.y, c.y); hi.z = fmaxf(hi.z, c.z);
-        }
-    }
-    store_child_box(nodes + (size_t)seg * sh.nodes_per_seg + sh.level_off[1] + (g >> ICP_LOG_FAN), g & (ICP_FAN - 1), lo, hi);
 }
 
 // level >= 1 (below the root): union of the node's own 8 child boxes goes into its parent's record
@@ -675,6 +607,84 @@ __global__ void __launch_bounds__(256) upper_box_kernel(WideNode* __restrict__ n
         hi.x = fmaxf(hi.x, me->hix[k]); hi.y = fmaxf(hi.y, me->hiy[k]); hi.z = fmaxf(hi.z, me->hiz[k]);
     }
     store_child_box(base + parent_off + (i >> ICP_LOG_FAN), i & (ICP_FAN - 1), lo, hi);
+}
+
+// One warp per 32-point unit, one pass over the final order: the inverse permutation
+// (pos_of_orig), the split mask of the unit (rule above) and the tight boxes of its four leaf groups,
+// written into slot g&7 of record (1, g>>3).
+__global__ void __launch_bounds__(256) finish_units_kernel(const float4* __restrict__ pts, const uint32_t* __restrict__ counts,
+                                                           TreeShape sh, uint32_t nseg, uint32_t* __restrict__ pos_of_orig,
+                                                           uint32_t* __restrict__ unit_split, WideNode* __restrict__ nodes) {
+    const size_t wid = ((size_t)blockIdx.x * 256 + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    if (wid >= (size_t)nseg * sh.units_per_seg) return;
+    const uint32_t seg = (uint32_t)(wid / sh.units_per_seg), unit = (uint32_t)(wid - (size_t)seg * sh.units_per_seg);
+    const uint32_t i = unit * 32u + lane;
+    const bool in_pitch = i < sh.pitch;
+    float4 p = make_float4(0.f, 0.f, 0.f, __uint_as_float((uint32_t)ICP_INVALID_ID));
+    if (in_pitch) p = pts[(size_t)seg * sh.pitch + i];
+    const bool act = in_pitch && i < counts[seg] && __float_as_uint(p.w) != (uint32_t)ICP_INVALID_ID;
+    if (act) pos_of_orig[(size_t)seg * sh.pitch + __float_as_uint(p.w)] = i;
+    // ---- split mask ----
+    const uint32_t none_lo = 0xffffffffu, none_hi = 0u;
+    const uint32_t ox = float_to_ordered(p.x), oy = float_to_ordered(p.y), oz = float_to_ordered(p.z);
+    const float lx = ordered_to_float(__reduce_min_sync(0xffffffffu, act ? ox : none_lo)), hx = ordered_to_float(__reduce_max_sync(0xffffffffu, act ? ox : none_hi));
+    const float ly = ordered_to_float(__reduce_min_sync(0xffffffffu, act ? oy : none_lo)), hy = ordered_to_float(__reduce_max_sync(0xffffffffu, act ? oy : none_hi));
+    const float lz = ordered_to_float(__reduce_min_sync(0xffffffffu, act ? oz : none_lo)), hz = ordered_to_float(__reduce_max_sync(0xffffffffu, act ? oz : none_hi));
+    uint32_t mask = 0u;
+    if (__popc(__ballot_sync(0xffffffffu, act)) >= 2) {
+        const float ex = hx - lx, ey = hy - ly, ez = hz - lz;
+        const float c = (ex >= ey && ex >= ez) ? p.x : (ey >= ez ? p.y : p.z);
+        const float mid = (ex >= ey && ex >= ez) ? 0.5f * (lx + hx) : (ey >= ez ? 0.5f * (ly + hy) : 0.5f * (lz + hz));
+        const bool g1 = act && c > mid, g0 = act && !g1;
+        float d2[2];
+#pragma unroll
+        for (int g = 0; g < 2; g++) {
+            const bool in = g ? g1 : g0;
+            const float ax = ordered_to_float(__reduce_max_sync(0xffffffffu, in ? ox : none_hi)) - ordered_to_float(__reduce_min_sync(0xffffffffu, in ? ox : none_lo));
+            const float ay = ordered_to_float(__reduce_max_sync(0xffffffffu, in ? oy : none_hi)) - ordered_to_float(__reduce_min_sync(0xffffffffu, in ? oy : none_lo));
+            const float az = ordered_to_float(__reduce_max_sync(0xffffffffu, in ? oz : none_hi)) - ordered_to_float(__reduce_min_sync(0xffffffffu, in ? oz : none_lo));
+            d2[g] = ax * ax + ay * ay + az * az;
+        }
+        const uint32_t m1 = __ballot_sync(0xffffffffu, g1), m0 = __ballot_sync(0xffffffffu, g0);
+        const float whole = ex * ex + ey * ey + ez * ez;
+        if (m0 && m1 && fmaxf(d2[0], d2[1]) * ICP_SPLIT_RATIO2 < whole) mask = m1;
+    }
+    if (lane == 0) unit_split[(size_t)seg * sh.units_per_seg + unit] = mask;
+    // ---- leaf boxes: lanes 8j .. 8j+7 hold leaf group i / 8 ----
+    if (!nodes) return;
+    const float inf = __int_as_float(0x7f800000);
+    float3 lo = act ? make_float3(p.x, p.y, p.z) : make_float3(inf, inf, inf);
+    float3 hi = act ? make_float3(p.x, p.y, p.z) : make_float3(-inf, -inf, -inf);
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+        lo.x = fminf(lo.x, __shfl_xor_sync(0xffffffffu, lo.x, o)); lo.y = fminf(lo.y, __shfl_xor_sync(0xffffffffu, lo.y, o)); lo.z = fminf(lo.z, __shfl_xor_sync(0xffffffffu, lo.z, o));
+        hi.x = fmaxf(hi.x, __shfl_xor_sync(0xffffffffu, hi.x, o)); hi.y = fmaxf(hi.y, __shfl_xor_sync(0xffffffffu, hi.y, o)); hi.z = fmaxf(hi.z, __shfl_xor_sync(0xffffffffu, hi.z, o));
+    }
+    if ((lane & 7u) == 0u && in_pitch) {
+        const uint32_t g = i >> ICP_LOG_LEAF;
+        store_child_box(nodes + (size_t)seg * sh.nodes_per_seg + sh.level_off[1] + (g >> ICP_LOG_FAN), g & (ICP_FAN - 1), lo, hi);
+    }
+}
+
+// levels first_level .. root-1 of one segment in one block (they hold a few thousand nodes at most): every
+// node's own 8 child boxes are united into its parent's record, level by level
+__global__ void __launch_bounds__(256) upper_levels_kernel(WideNode* __restrict__ nodes, TreeShape sh, uint32_t first_level) {
+    WideNode* base = nodes + (size_t)blockIdx.x * sh.nodes_per_seg;
+    const float inf = __int_as_float(0x7f800000);
+    for (uint32_t l = first_level; l + 1 < sh.n_levels; l++) {
+        for (uint32_t i = threadIdx.x; i < sh.level_cnt[l]; i += 256) {
+            const WideNode* me = base + sh.level_off[l] + i;
+            float3 lo = make_float3(inf, inf, inf), hi = make_float3(-inf, -inf, -inf);
+#pragma unroll
+            for (int k = 0; k < ICP_FAN; k++) {
+                lo.x = fminf(lo.x, me->lox[k]); lo.y = fminf(lo.y, me->loy[k]); lo.z = fminf(lo.z, me->loz[k]);
+                hi.x = fmaxf(hi.x, me->hix[k]); hi.y = fmaxf(hi.y, me->hiy[k]); hi.z = fmaxf(hi.z, me->hiz[k]);
+            }
+            store_child_box(base + sh.level_off[l + 1] + (i >> ICP_LOG_FAN), i & (ICP_FAN - 1), lo, hi);
+        }
+        __syncthreads();   // the next level reads what this one wrote (same block)
+    }
 }
 
 inline uint32_t round_up(uint32_t v, uint32_t m) { return (v + m - 1) / m * m; }
@@ -882,22 +892,18 @@ int icp_build_cloudset(icpsymm_ctx* ctx, CloudSet& cs, const float* xyz, bool on
         const uint32_t wins = sh.pitch / 512;
         if (wins) kd_refine_kernel<512><<<ns * wins, 256, 0, st>>>(cs.pts, cs.counts, sh.pitch, wins);
     }
-    inverse_perm_kernel<<<gb, 256, 0, st>>>(cs.pts, cs.counts, sh.pitch, ns, cs.pos_of_orig);
-    {
-        size_t thr = (size_t)ns * sh.units_per_seg * 32;
-        unit_split_kernel<<<(uint32_t)((thr + 255) / 256), 256, 0, st>>>(cs.pts, cs.counts, sh.pitch, sh.units_per_seg, ns, cs.unit_split);
-    }
     {
         size_t nfl = nodes * 48;
         init_nodes_kernel<<<(uint32_t)((nfl + 255) / 256), 256, 0, st>>>(cs.nodes, nfl);
-        if (sh.n_levels > 1) {
-            size_t n0 = (size_t)ns * (sh.pitch / ICP_LEAF);
-            leaf_box_kernel<<<(uint32_t)((n0 + 255) / 256), 256, 0, st>>>(cs.pts, cs.nodes, sh, ns);
-            for (uint32_t l = 1; l + 1 < sh.n_levels; l++) {
-                size_t nl = (size_t)ns * sh.level_cnt[l];
-                upper_box_kernel<<<(uint32_t)((nl + 255) / 256), 256, 0, st>>>(cs.nodes, sh, ns, (int)l, sh.level_off[l],
-                                                                               sh.level_cnt[l], sh.level_off[l + 1]);
-            }
+        const size_t thr = (size_t)ns * sh.units_per_seg * 32;
+        finish_units_kernel<<<(uint32_t)((thr + 255) / 256), 256, 0, st>>>(cs.pts, cs.counts, sh, ns, cs.pos_of_orig, cs.unit_split,
+                                                                           sh.n_levels > 1 ? cs.nodes : nullptr);
+        if (sh.n_levels > 2) {
+            // level 1 is the large one (pitch / 64 nodes): all blocks; the levels above it: one block per segment
+            const size_t nl = (size_t)ns * sh.level_cnt[1];
+            upper_box_kernel<<<(uint32_t)((nl + 255) / 256), 256, 0, st>>>(cs.nodes, sh, ns, 1, sh.level_off[1], sh.level_cnt[1],
+                                                                           sh.level_off[2]);
+            if (sh.n_levels > 3) upper_levels_kernel<<<ns, 256, 0, st>>>(cs.nodes, sh, 2u);
         }
     }
     ICP_CUDA_CHECK(cudaMemsetAsync(cs.nrm, 0, slots * sizeof(float4), st));

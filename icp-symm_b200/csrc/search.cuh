@@ -234,7 +234,7 @@ __device__ __forceinline__ void wide_traverse_group(const TreeShape& sh, const W
     }
 }
 
-// split_mask != 0 (warp-uniform): the unit holds two far-apart clusters (index build, unit_split_kernel);
+// split_mask != 0 (warp-uniform): the unit holds two far-apart clusters (index build, finish_units_kernel);
 // the lanes of each cluster walk the hierarchy on their own, so that each walk sees a compact patch.
 template <typename V>
 __device__ __forceinline__ void wide_traverse_warp(const TreeShape& sh, const WideNode* __restrict__ seg_nodes,
