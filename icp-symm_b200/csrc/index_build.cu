@@ -669,11 +669,11 @@ __global__ void __launch_bounds__(256) finish_units_kernel(const float4* __restr
 
 // levels first_level .. root-1 of one segment in one block (they hold a few thousand nodes at most): every
 // node's own 8 child boxes are united into its parent's record, level by level
-__global__ void __launch_bounds__(256) upper_levels_kernel(WideNode* __restrict__ nodes, TreeShape sh, uint32_t first_level) {
+__global__ void __launch_bounds__(512) upper_levels_kernel(WideNode* __restrict__ nodes, TreeShape sh, uint32_t first_level) {
     WideNode* base = nodes + (size_t)blockIdx.x * sh.nodes_per_seg;
     const float inf = __int_as_float(0x7f800000);
     for (uint32_t l = first_level; l + 1 < sh.n_levels; l++) {
-        for (uint32_t i = threadIdx.x; i < sh.level_cnt[l]; i += 256) {
+        for (uint32_t i = threadIdx.x; i < sh.level_cnt[l]; i += blockDim.x) {
             const WideNode* me = base + sh.level_off[l] + i;
             float3 lo = make_float3(inf, inf, inf), hi = make_float3(-inf, -inf, -inf);
 #pragma unroll
@@ -898,13 +898,15 @@ int icp_build_cloudset(icpsymm_ctx* ctx, CloudSet& cs, const float* xyz, bool on
         const size_t thr = (size_t)ns * sh.units_per_seg * 32;
         finish_units_kernel<<<(uint32_t)((thr + 255) / 256), 256, 0, st>>>(cs.pts, cs.counts, sh, ns, cs.pos_of_orig, cs.unit_split,
                                                                            sh.n_levels > 1 ? cs.nodes : nullptr);
-        if (sh.n_levels > 2) {
-            // level 1 is the large one (pitch / 64 nodes): all blocks; the levels above it: one block per segment
-            const size_t nl = (size_t)ns * sh.level_cnt[1];
-            upper_box_kernel<<<(uint32_t)((nl + 255) / 256), 256, 0, st>>>(cs.nodes, sh, ns, 1, sh.level_off[1], sh.level_cnt[1],
-                                                                           sh.level_off[2]);
-            if (sh.n_levels > 3) upper_levels_kernel<<<ns, 256, 0, st>>>(cs.nodes, sh, 2u);
+        // large levels: one thread per node over the whole grid; the small ones at the top (at most 512 nodes
+        // each): together in one block per segment
+        uint32_t l = 1;
+        for (; l + 1 < sh.n_levels && sh.level_cnt[l] > 512; l++) {
+            const size_t nl = (size_t)ns * sh.level_cnt[l];
+            upper_box_kernel<<<(uint32_t)((nl + 255) / 256), 256, 0, st>>>(cs.nodes, sh, ns, (int)l, sh.level_off[l],
+                                                                           sh.level_cnt[l], sh.level_off[l + 1]);
         }
+        if (l + 1 < sh.n_levels) upper_levels_kernel<<<ns, 512, 0, st>>>(cs.nodes, sh, l);
     }
     ICP_CUDA_CHECK(cudaMemsetAsync(cs.nrm, 0, slots * sizeof(float4), st));
     ICP_CUDA_CHECK(cudaGetLastError());
