@@ -294,7 +294,7 @@ def main():
             "clocks": clocks,
             "e2e": {"value": tot_e2e_corr / (max_e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": max_e2e_ms / args.steps,
                     "h2d_bytes_per_step": int(2 * n * 12), "d2h_bytes_per_step": 64 + 2 * 128,
-                    "includes": "H2D of both clouds, Morton sort + box hierarchy, kNN-10 normals, loop, D2H transform"},
+                    "includes": "H2D of both clouds, Hilbert sort + k-d refinement + box hierarchy, kNN-10 normals, loop, D2H transform"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "nn_accum_kernel (fused NN search + symmetric accumulate)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
