@@ -15,8 +15,9 @@
 //                          theta = atan|a| and the half-rotation composition (func.cpp:91-99, in
 //                          the order of the comment at :94), transform = incre * transform
 //                          (myicp.cpp:138).
-// The whole loop ((max_iters+1) x [K1,K2]) is captured once as a CUDA graph; a device-side `done`
-// flag in SegState turns the remaining launches into early exits once a pair has converged.
+// The loop is one CUDA graph whose WHILE node repeats [K1,K2] until K2 clears the condition on the
+// device (default), or an unrolled graph of (max_iters+1) x [K1,K2] in which a device-side `done`
+// flag in SegState turns the remaining launches into early exits, or plain stream launches.
 #include <cmath>
 #include <cstdio>
 #include <cstring>
