@@ -127,7 +127,7 @@ int icpsymm_set_option(icpsymm_ctx* ctx, int key, double value) {
         case ICPSYMM_OPT_MIN_NORMAL_DOT: ctx->opt_min_normal_dot = (value <= -1.0) ? -2.f : (float)value; break;
         case ICPSYMM_OPT_USE_GRAPH: ctx->opt_use_graph = (value == 2) ? 2 : (value != 0); break;
         case ICPSYMM_OPT_KERNEL_TIMING: ctx->opt_kernel_timing = value != 0; break;
-        case ICPSYMM_OPT_WARM_START: ctx->opt_warm_start = value != 0; break;
+        case ICPSYMM_OPT_WARM_START: ctx->opt_warm_start = (value == 2) ? 2 : (value != 0); break;
         case ICPSYMM_OPT_TRACE: ctx->opt_trace = value != 0; break;
         case ICPSYMM_OPT_GRID_BLOCKS: if (value < 0) return ICPSYMM_ERR_INVALID; ctx->opt_grid_blocks = (int)value; break;
         case ICPSYMM_OPT_ASYNC_SETUP: {
@@ -136,6 +136,7 @@ int icpsymm_set_option(icpsymm_ctx* ctx, int key, double value) {
             if (jr < 0) return jr;
             break;
         }
+        case ICPSYMM_OPT_PEER_TIMEOUT_MS: if (!(value > 0)) return ICPSYMM_ERR_INVALID; ctx->opt_peer_timeout_ms = value; break;
         default: return icp_fail_msg(ctx, ICPSYMM_ERR_INVALID, "unknown option key");
     }
     return ICPSYMM_OK;

@@ -134,6 +134,10 @@ extern "C" int icpsymm_peer_attach(icpsymm_ctx* ctx, const void* handles, int n_
     ctx->peer_world = n_ranks;
     ctx->shard_rank = rank;
     ctx->shard_world = n_ranks;
+    // a fresh exchange: every rank starts at sequence 0 with zeroed slots (attach is collective: all ranks
+    // export, gather the handles and attach; re-attaching needs a detach on every rank first)
+    if (ctx->d_ctrl) ICP_CUDA_CHECK(cudaMemsetAsync(ctx->d_ctrl, 0, sizeof(LoopCtrl), ctx->stream));
+    ICP_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     // the captured loop graph holds the old peer pointers
     if (ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }
     return ICPSYMM_OK;
@@ -150,6 +154,8 @@ extern "C" int icpsymm_peer_detach(icpsymm_ctx* ctx) {
     if (ctx->peer_local) { cudaFree(ctx->peer_local); ctx->peer_local = nullptr; }
     if (ctx->peer_world > 1) { ctx->shard_rank = 0; ctx->shard_world = 1; }
     ctx->peer_world = 0;
+    if (ctx->d_ctrl) cudaMemsetAsync(ctx->d_ctrl, 0, sizeof(LoopCtrl), ctx->stream);   // sequence, error flag, tickets
+    cudaStreamSynchronize(ctx->stream);
     if (ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }
     cudaGetLastError();
     return ICPSYMM_OK;

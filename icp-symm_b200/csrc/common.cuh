@@ -41,6 +41,15 @@ struct __align__(128) PeerSlot {
     unsigned long long pad[7];
 };
 
+// control words of the device-side loop (one per context)
+struct LoopCtrl {
+    unsigned int ticket;      // blocks of K2 that have arrived in this iteration
+    unsigned int done_count;  // pairs that are finished (now or earlier) in this iteration
+    unsigned long long seq;   // number of peer exchanges done so far (identical on every rank)
+    int comm_error;           // a peer did not answer in time
+    int pad;
+};
+
 // boxes of the 8 children of one internal node, structure-of-arrays so that one node is 12
 // independent 16-byte loads and the 8 bounds are computed together
 struct __align__(16) WideNode {

@@ -56,7 +56,11 @@ extern "C" int icpsymm_debug_k1_times(unsigned long long* out, int n) {
 
 namespace {
 
-constexpr int kNNThreads = 256;
+#ifndef ICP_K1_THREADS
+#define ICP_K1_THREADS 256
+#endif
+constexpr int kNNThreads = ICP_K1_THREADS;
+constexpr int kNNBlocksPerSM = 1024 / kNNThreads;   // 64 registers per thread: 1024 threads per SM
 constexpr int kNNWarps = kNNThreads / 32;
 #ifndef ICP_K2_THREADS
 #define ICP_K2_THREADS 1024
@@ -77,14 +81,6 @@ struct NNParams {
     int shard_rank, shard_world;
 };
 
-struct LoopCtrl {
-    unsigned int ticket;      // blocks of K2 that have arrived in this iteration
-    unsigned int done_count;  // pairs that are finished (now or earlier) in this iteration
-    unsigned long long seq;   // number of peer exchanges done so far (identical on every rank)
-    int comm_error;           // a peer did not answer in time
-    int pad;
-};
-
 struct SolveParams {
     cudaGraphConditionalHandle cond;   // while-node condition (use_cond != 0)
     LoopCtrl* ctrl;
@@ -100,6 +96,7 @@ struct SolveParams {
     int mode;  // 0 reduce+solve, 1 reduce only (-> gsum), 2 solve from gsum, 3 reduce + record, no solve
     PeerSlot* peers[ICP_MAX_PEERS];   // NVLink peer mode: exchange buffers of all ranks (mine included)
     int peer_world, peer_rank;
+    unsigned long long peer_timeout_ns;
 };
 
 struct InitArgs {
@@ -133,7 +130,7 @@ __global__ void init_state_kernel(SegState* state, uint32_t nseg, InitArgs a, co
 // ------------------------------------------------------------------------------------------------
 // K1: search + accumulate
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kNNThreads, 4) nn_accum_kernel(const __grid_constant__ NNParams P) {
+__global__ void __launch_bounds__(kNNThreads, kNNBlocksPerSM) nn_accum_kernel(const __grid_constant__ NNParams P) {
 #ifdef ICP_BLOCK_TIMES
     K1Timer timer_;
 #endif
@@ -525,9 +522,11 @@ __global__ void __launch_bounds__(kSolveThreads) solve_kernel(const __grid_const
                 __threadfence_system();
                 // wait until rank `tid` has published this iteration into MY buffer
                 volatile unsigned long long* mine = &P.peers[P.peer_rank][par * ICP_MAX_PEERS + tid].seq;
-                const long long t0 = clock64();
-                while (*mine != seq) {
-                    if (clock64() - t0 > 4000000000ll) { P.ctrl->comm_error = 1; break; }   // ~2 s: never hang the GPU
+                unsigned long long t0, t1;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+                while (*mine != seq) {   // bounded: a rank that never publishes must not hang the GPU
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                    if (t1 - t0 > P.peer_timeout_ns) { P.ctrl->comm_error = 1; break; }
                 }
                 __threadfence_system();
             }
@@ -661,7 +660,7 @@ static uint32_t choose_blocks_per_seg(const icpsymm_ctx* ctx, uint32_t nseg, uin
     uint32_t bps;
     if (ctx->opt_grid_blocks > 0) bps = (uint32_t)ctx->opt_grid_blocks;
     else {
-        const uint32_t resident = (uint32_t)ctx->sm_count * 4u;   // 4 blocks per SM
+        const uint32_t resident = (uint32_t)ctx->sm_count * (uint32_t)kNNBlocksPerSM;   // resident blocks
         uint32_t target = resident * 4u;                          // 4 waves: measured best at 1M and beyond
         // between one and two tiles per block the blocks with two tiles (lowest indices) start first and
         // the one-tile blocks fill the tail; about 3/4 of the tile count, rounded to whole waves, balances
@@ -755,10 +754,8 @@ int icp_run_loop(icpsymm_ctx* ctx, int max_iters, float thr, const float* T_init
     const int n_search = single_search ? 1 : max_iters + 1;
     if (ctx->opt_trace) {
         size_t need = (size_t)nseg * n_search;
-        size_t c1 = ctx->trace_cap, c2 = ctx->trace_cap;
-        if ((rc = icp_reserve(ctx, &ctx->trace_T, &c1, need * 12))) return rc;
-        if ((rc = icp_reserve(ctx, &ctx->trace_diff, &c2, need))) return rc;
-        ctx->trace_cap = c2 < c1 / 12 ? c2 : c1 / 12;
+        if ((rc = icp_reserve(ctx, &ctx->trace_T, &ctx->trace_T_cap, need * 12))) return rc;
+        if ((rc = icp_reserve(ctx, &ctx->trace_diff, &ctx->trace_diff_cap, need))) return rc;
         ctx->trace_stride = n_search;
     }
 
@@ -784,7 +781,10 @@ int icp_run_loop(icpsymm_ctx* ctx, int max_iters, float thr, const float* T_init
         for (int i = 0; i < 3; i++) ia.origin[i] = origin[i];
     }
     init_state_kernel<<<(nseg + 127) / 128, 128, 0, st>>>(ctx->d_state, nseg, ia, T.bb_lo, T.bb_hi);
-    ICP_CUDA_CHECK(cudaMemsetAsync(ctx->corr_pos, 0xff, sizeof(uint32_t) * (size_t)nseg * S.shape.pitch, st));
+    // ICPSYMM_OPT_WARM_START = 2 keeps the correspondences of the previous call as seeds of the first search
+    // (frame-to-frame tracking); a seed is only ever a candidate, so the result stays exact
+    if (!(ctx->opt_warm_start == 2 && ctx->have_corr))
+        ICP_CUDA_CHECK(cudaMemsetAsync(ctx->corr_pos, 0xff, sizeof(uint32_t) * (size_t)nseg * S.shape.pitch, st));
 
     NNParams np;
     np.src = S.view(); np.tgt = T.view();
@@ -800,7 +800,10 @@ int icp_run_loop(icpsymm_ctx* ctx, int max_iters, float thr, const float* T_init
         ICP_CUDA_CHECK(cudaMemsetAsync(ctx->d_ctrl, 0, sizeof(LoopCtrl), st));
     }
     sp.ctrl = (LoopCtrl*)ctx->d_ctrl; sp.use_cond = 0; sp.cond = 0;
-    sp.peer_world = ctx->peer_world; sp.peer_rank = ctx->shard_rank;
+    // single searches (find_correspondences, eval_diff, normal_equations) are LOCAL to the rank's shard: only
+    // the registration loop is collective, so one rank may call them without stalling on its peers
+    sp.peer_world = single_search ? 0 : ctx->peer_world; sp.peer_rank = ctx->shard_rank;
+    sp.peer_timeout_ns = (unsigned long long)(ctx->opt_peer_timeout_ms * 1e6);
     for (int r = 0; r < ICP_MAX_PEERS; r++) sp.peers[r] = (PeerSlot*)ctx->peer_ptrs[r];
     if (ctx->peer_world > 1 && nseg != 1)
         return icp_fail_msg(ctx, ICPSYMM_ERR_INVALID, "the NVLink peer exchange supports single pairs only");
@@ -825,11 +828,10 @@ int icp_run_loop(icpsymm_ctx* ctx, int max_iters, float thr, const float* T_init
         GraphKey key;
         key.max_iters = max_iters; key.nseg = nseg; key.blocks_per_seg = bps;
         key.src_pitch = S.shape.pitch; key.tgt_pitch = T.shape.pitch;
-        key.p0 = S.pts; key.p1 = T.pts; key.p2 = ctx->partial; key.p3 = ctx->corr_pos; key.p4 = ctx->d_state;
-        key.p5 = ctx->opt_trace ? (const void*)ctx->trace_T : (const void*)T.nodes;
+        key.generation = ctx->generation;
         key.shard_rank = ctx->shard_rank; key.shard_world = ctx->shard_world; key.trace = ctx->opt_trace;
+        key.trace_stride = ctx->opt_trace ? ctx->trace_stride : 0;
         key.mode = ctx->opt_use_graph + 16 * ctx->peer_world;
-        // pointers of the remaining arrays change only together with the ones above (same reserve calls)
         if (!ctx->graph_exec || !(ctx->graph_key == key)) {
             if (ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }
             cudaGraph_t g = nullptr;
@@ -877,7 +879,12 @@ int icp_run_loop(icpsymm_ctx* ctx, int max_iters, float thr, const float* T_init
     if (ctx->peer_world > 1) {
         LoopCtrl hc;
         ICP_CUDA_CHECK(cudaMemcpy(&hc, ctx->d_ctrl, sizeof hc, cudaMemcpyDeviceToHost));
-        if (hc.comm_error) return icp_fail_msg(ctx, ICPSYMM_ERR_COMM, "peer exchange timed out: a rank did not publish its sums");
+        if (hc.comm_error) {
+            // report once and clear, so that the context is usable again after the peers have re-attached
+            ICP_CUDA_CHECK(cudaMemsetAsync(&((LoopCtrl*)ctx->d_ctrl)->comm_error, 0, sizeof(int), st));
+            return icp_fail_msg(ctx, ICPSYMM_ERR_COMM, "peer exchange timed out: a rank did not publish its sums "
+                                                      "(all ranks must detach and attach again before the next sharded registration)");
+        }
     }
 
     float loop_ms = 0.f;
@@ -913,7 +920,7 @@ int icp_run_loop(icpsymm_ctx* ctx, int max_iters, float thr, const float* T_init
             if (ctx->shard_world > 1) {
                 uint32_t lo = (uint32_t)(((unsigned long long)nq * ctx->shard_rank) / ctx->shard_world);
                 uint32_t hi = (uint32_t)(((unsigned long long)nq * (ctx->shard_rank + 1)) / ctx->shard_world);
-                nq = use_comm ? nq : hi - lo;
+                nq = (use_comm || (ctx->peer_world > 1 && !single_search)) ? nq : hi - lo;   // global sums: all source points
             }
             o.rmse = nq ? sqrt(hs.sumd2 / (double)nq) : 0.0;
             o.min_pivot_ratio = hs.min_ratio; o.pairs = hs.pairs;
@@ -1005,3 +1012,45 @@ int icp_solve_compose_device(icpsymm_ctx* ctx, const double* sums, const double*
     if (ratio) *ratio = out[18];
     return out[19] != 0.0 ? ICPSYMM_WARN_DEGENERATE : ICPSYMM_OK;
 }
+
+#ifdef ICP_EXPERIMENT   // developer build only (make exp): seed-quality experiments, never in the shipped library
+namespace {
+__global__ void seed_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint32_t n, int mode) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t j = i;
+    switch (mode) {
+        case 1: j = i; break;                                   // own neighbour: perfect bound
+        case 2: j = (i & ~31u) + 16u; break;                    // the unit centre's neighbour
+        case 3: j = i >= 32u ? i - 32u : i; break;              // same lane of the previous unit
+        case 4: j = i >= 256u ? i - 256u : i; break;            // same lane, previous 256-point tile
+        case 5: j = i >= 32u ? ((i - 32u) & ~31u) + 16u : i; break;   // centre of the previous unit
+        case 6: j = (i & ~255u) + 128u; break;                  // one probe per 256 points
+        case 7: j = (i & ~1023u) + 512u; break;                 // one probe per 1024 points
+        case 8: j = (i & ~7u) + 4u; break;                      // one probe per leaf group
+    }
+    if (j >= n) j = i;
+    out[i] = mode == 0 ? 0xffffffffu : in[j];
+}
+}
+extern "C" int icpsymm_debug_seed(icpsymm_ctx* ctx, int mode) {
+    // mode -1: back up the current correspondences; mode >= 0: corr = f_mode(backup)
+    static uint32_t* backup = nullptr; static size_t cap = 0;
+    const size_t n = (size_t)ctx->src.shape.pitch;
+    if (n > cap) { cudaFree(backup); cudaMalloc(&backup, n * 4); cap = n; }
+    if (mode < 0) return (int)cudaMemcpyAsync(backup, ctx->corr_pos, n * 4, cudaMemcpyDeviceToDevice, ctx->stream);
+    seed_kernel<<<(uint32_t)((n + 255) / 256), 256, 0, ctx->stream>>>(backup, ctx->corr_pos, ctx->src.h_counts[0], mode);
+    ctx->have_corr = true;
+    return (int)cudaGetLastError();
+}
+extern "C" int icpsymm_debug_single_search(icpsymm_ctx* ctx, const float* T16, icpsymm_stats* stats) {
+    return icp_run_single(ctx, T16, nullptr, stats);
+}
+extern "C" int icpsymm_debug_search_times(icpsymm_ctx* ctx, float* search_ms, float* solve_ms, int n) {
+    for (int k = 0; k < n && 4 * k + 3 < ctx->ev_pool_n; k++) {
+        cudaEventElapsedTime(search_ms + k, ctx->ev_pool[4 * k], ctx->ev_pool[4 * k + 1]);
+        cudaEventElapsedTime(solve_ms + k, ctx->ev_pool[4 * k + 2], ctx->ev_pool[4 * k + 3]);
+    }
+    return 0;
+}
+#endif

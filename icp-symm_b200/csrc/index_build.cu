@@ -698,6 +698,7 @@ int icp_reserve(icpsymm_ctx* ctx, T** p, size_t* cap, size_t need) {
     size_t n = need ? need : 1;
     ICP_CUDA_CHECK(cudaMalloc((void**)p, n * sizeof(T)));
     *cap = n;
+    if (ctx) ctx->generation++;   // captured graphs hold the old pointer
     return ICPSYMM_OK;
 }
 template int icp_reserve<float4>(icpsymm_ctx*, float4**, size_t*, size_t);

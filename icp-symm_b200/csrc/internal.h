@@ -41,13 +41,15 @@ struct CloudSet {
 struct GraphKey {
     int max_iters = -1;
     uint32_t nseg = 0, blocks_per_seg = 0, src_pitch = 0, tgt_pitch = 0;
-    const void *p0 = nullptr, *p1 = nullptr, *p2 = nullptr, *p3 = nullptr, *p4 = nullptr, *p5 = nullptr;
-    int mode = 0, shard_rank = 0, shard_world = 1, trace = 0;   // mode: graph flavour + peer world
+    // every device pointer the captured kernels hold belongs to this context; `generation` counts the
+    // (re)allocations of all of them, so an unchanged generation means unchanged pointers
+    unsigned long long generation = ~0ull;
+    int mode = 0, shard_rank = 0, shard_world = 1, trace = 0, trace_stride = 0;   // mode: graph flavour + peer world
     bool operator==(const GraphKey& o) const {
         return max_iters == o.max_iters && nseg == o.nseg && blocks_per_seg == o.blocks_per_seg &&
-               src_pitch == o.src_pitch && tgt_pitch == o.tgt_pitch && p0 == o.p0 && p1 == o.p1 && p2 == o.p2 &&
-               p3 == o.p3 && p4 == o.p4 && p5 == o.p5 && mode == o.mode && shard_rank == o.shard_rank &&
-               shard_world == o.shard_world && trace == o.trace;
+               src_pitch == o.src_pitch && tgt_pitch == o.tgt_pitch && generation == o.generation && mode == o.mode &&
+               shard_rank == o.shard_rank && shard_world == o.shard_world && trace == o.trace &&
+               trace_stride == o.trace_stride;
     }
 };
 
@@ -85,7 +87,9 @@ struct icpsymm_ctx {
     uint32_t* corr_pos = nullptr; size_t corr_cap = 0;
     double* partial = nullptr;    size_t partial_cap = 0;
     double* gsum = nullptr;       size_t gsum_cap = 0;
-    float* trace_T = nullptr;     double* trace_diff = nullptr; size_t trace_cap = 0; int trace_stride = 0;
+    float* trace_T = nullptr;     size_t trace_T_cap = 0;      // floats
+    double* trace_diff = nullptr; size_t trace_diff_cap = 0;   // doubles
+    int trace_stride = 0;
     void* io_buf = nullptr;       size_t io_bytes = 0;   // device scratch for exports/imports
     bool have_corr = false;
 
@@ -100,8 +104,10 @@ struct icpsymm_ctx {
     int opt_trace = 0;
     int opt_grid_blocks = 0;
     int opt_async_setup = 0;
+    double opt_peer_timeout_ms = 10000.0;
 
     // graph cache
+    unsigned long long generation = 0;   // bumped by every device (re)allocation of this context (icp_reserve)
     cudaGraphExec_t graph_exec = nullptr;
     GraphKey graph_key;
 

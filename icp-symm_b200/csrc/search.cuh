@@ -61,6 +61,33 @@ __device__ __forceinline__ void scan_leaf(const float4* __restrict__ seg_pts, ui
     for (int j = 0; j < ICP_LEAF; j++) best_offer_packed(b, c[j], nq);
 }
 
+// Warp-uniform leaf scan that builds the 64-bit (d2, index) keys only when some lane can use them: the 8
+// squared distances and their minimum are plain fp32 work (FMNMX3); a point can replace a lane's best only
+// when its d2 does not exceed the lane's bound (equal d2: the lower original index wins), so when no
+// taking lane has min d2 <= bound the scan changes nothing.  Returns whether some taking lane's bound
+// changed (warp-uniform).  `take` = false: the lane is a bystander and keeps its state.
+__device__ __forceinline__ bool scan_leaf_lazy(const float4* __restrict__ seg_pts, uint32_t g, const NegQuery& nq,
+                                               bool take, Best& b) {
+    const float4* lp = seg_pts + (size_t)g * ICP_LEAF;
+    float4 c[ICP_LEAF];
+    float d[ICP_LEAF];
+#pragma unroll
+    for (int j = 0; j < ICP_LEAF; j++) c[j] = ldg4(lp + j);
+#pragma unroll
+    for (int j = 0; j < ICP_LEAF; j++) d[j] = dist2_packed(nq, c[j]);
+    const float m = fminf(fminf(fminf(d[0], d[1]), fminf(d[2], d[3])), fminf(fminf(d[4], d[5]), fminf(d[6], d[7])));
+    const uint32_t bound = (uint32_t)(b.key >> 32);
+    if (!__any_sync(0xffffffffu, take && __float_as_uint(m) <= bound)) return false;
+    if (take) {
+#pragma unroll
+        for (int j = 0; j < ICP_LEAF; j++) {
+            const unsigned long long k = ((unsigned long long)__float_as_uint(d[j]) << 32) | __float_as_uint(c[j].w);
+            b.key = k < b.key ? k : b.key;
+        }
+    }
+    return __any_sync(0xffffffffu, take && (uint32_t)(b.key >> 32) != bound);
+}
+
 // Warp-synchronous variant: the 32 lanes hold 32 neighbouring queries (consecutive points of the
 // Hilbert-sorted source, a compact patch after any rigid transform) and walk the hierarchy
 // TOGETHER, so node records and leaf points are warp-uniform loads and nothing diverges: the warp
@@ -177,11 +204,13 @@ __device__ __forceinline__ bool warp_child_recheck(const WideNode* __restrict__ 
     return __any_sync(0xffffffffu, active && lb <= my_bound && lb != ICP_INF_BITS);
 }
 
+// The pending mask and the record pointer of the CURRENT node live in registers: a pop touches only
+// those; the 64-bit store of the ancestors' masks is read and written once per node entered or left.
 template <typename V>
 __device__ __forceinline__ void wide_traverse_group(const TreeShape& sh, const WideNode* __restrict__ seg_nodes,
                                                     float qx, float qy, float qz, bool active, V& v) {
     const int top = (int)sh.n_levels - 1;
-    if (top == 0) { v.leaf(0); return; }
+    if (top == 0) { v.leaf(0, active); return; }
     if (!__any_sync(0xffffffffu, active)) return;
     const float inf = __uint_as_float(ICP_INF_BITS);
     WarpPatch pb;
@@ -192,47 +221,48 @@ __device__ __forceinline__ void wide_traverse_group(const TreeShape& sh, const W
     const float pdx = pb.hix - pb.lox, pdy = pb.hiy - pb.loy, pdz = pb.hiz - pb.loz;
     const uint32_t far_thr = __float_as_uint(ICP_FAR_FACTOR * (pdx * pdx + pdy * pdy + pdz * pdz));
     bool far_mode = max_bound > far_thr;
+    const WideNode* rec = seg_nodes + sh.level_off[top];
     uint32_t stale = 0;   // bit l: the pending mask of level l predates the latest bound improvement
     int l = top, pref;
     uint32_t i = 0;
-    unsigned long long masks =
-        (unsigned long long)warp_node_test(seg_nodes + sh.level_off[top], qx, qy, qz, v.bound_bits(), active, pb,
-                                           max_bound, far_mode, pref) << (8 * (top - 1));
+    uint32_t cur = warp_node_test(rec, qx, qy, qz, v.bound_bits(), active, pb, max_bound, far_mode, pref);
+    unsigned long long saved = 0ull;   // byte l-1: pending mask of the open ancestor at level l
     for (;;) {
-        const int sh8 = 8 * (l - 1);
-        const uint32_t m = (uint32_t)(masks >> sh8) & 0xffu;
-        if (m == 0) {
+        if (cur == 0u) {
             if (l == top) break;
             ++l; i >>= ICP_LOG_FAN;
+            const int sh8 = 8 * (l - 1);
+            cur = (uint32_t)(saved >> sh8) & 0xffu;
+            rec = seg_nodes + sh.level_off[l] + i;
             pref = -1;
             continue;
         }
-        const int c = (pref >= 0 && ((m >> pref) & 1u)) ? pref : (__ffs((int)m) - 1);
+        const int c = (pref >= 0 && ((cur >> pref) & 1u)) ? pref : (__ffs((int)cur) - 1);
         pref = -1;
-        masks &= ~(1ull << (sh8 + c));
-        const WideNode* rec = seg_nodes + sh.level_off[l] + i;
+        cur &= ~(1u << c);
         if (((stale >> l) & 1u) && !warp_child_recheck(rec, c, qx, qy, qz, v.bound_bits(), active)) continue;
         const uint32_t child = (i << ICP_LOG_FAN) + (uint32_t)c;
         ICP_ASSERT(l >= 1 && l <= top && i < sh.level_cnt[l] && child < sh.level_cnt[l - 1]);
+        bool improved = false;
         if (l == 1) {
             ICP_ASSERT(child < sh.pitch / ICP_LEAF);
-            const uint32_t before = v.bound_bits();
-            v.leaf(child);
-            const uint32_t after = v.bound_bits();
-            if (__any_sync(0xffffffffu, active && after != before)) {
-                stale = 0xffffffffu;
-                max_bound = __reduce_max_sync(0xffffffffu, active ? after : 0u);
-                far_mode = max_bound > far_thr;
-            }
+            improved = v.leaf(child, active);
         } else {
+            const int sh8 = 8 * (l - 1);
+            saved = (saved & ~(0xffull << sh8)) | ((unsigned long long)cur << sh8);
             --l; i = child;
-            const uint32_t cm = warp_node_test(seg_nodes + sh.level_off[l] + i, qx, qy, qz, v.bound_bits(), active, pb,
-                                               max_bound, far_mode, pref);
-            masks |= (unsigned long long)cm << (8 * (l - 1));
+            rec = seg_nodes + sh.level_off[l] + i;
+            cur = warp_node_test(rec, qx, qy, qz, v.bound_bits(), active, pb, max_bound, far_mode, pref);
             stale &= ~(1u << l);
+        }
+        if (improved) {   // some active lane's bound improved (warp-uniform)
+            stale = 0xffffffffu;
+            max_bound = __reduce_max_sync(0xffffffffu, active ? v.bound_bits() : 0u);
+            far_mode = max_bound > far_thr;
         }
     }
 }
+
 
 // split_mask != 0 (warp-uniform): the unit holds two far-apart clusters (index build, finish_units_kernel);
 // the lanes of each cluster walk the hierarchy on their own, so that each walk sees a compact patch.
@@ -253,9 +283,19 @@ struct NNVisitor {
     Best& b;
     const float4* __restrict__ pts;
     float qx, qy, qz;
+    NegQuery nq;
     __device__ __forceinline__ uint32_t bound_bits() const { return (uint32_t)(b.key >> 32); }
-    __device__ __forceinline__ void set_active(bool) {}   // a bystander lane only collects valid candidates
-    __device__ __forceinline__ void leaf(uint32_t g) { scan_leaf(pts, g, qx, qy, qz, b); }
+    __device__ __forceinline__ void set_active(bool) {}
+    // warp-uniform call; returns whether some active lane's bound changed
+    __device__ __forceinline__ bool leaf(uint32_t g, bool active) {
+#ifdef ICP_LEAF_EAGER
+        const uint32_t before = bound_bits();
+        scan_leaf(pts, g, qx, qy, qz, b);
+        return __any_sync(0xffffffffu, active && bound_bits() != before);
+#else
+        return scan_leaf_lazy(pts, g, nq, active, b);
+#endif
+    }
 };
 
 // full exact 1-NN search of all lanes of a warp; each `b` may already hold a candidate (warm start).
@@ -263,7 +303,7 @@ struct NNVisitor {
 __device__ __forceinline__ void nn_traverse_warp(const TreeShape& sh, const WideNode* __restrict__ seg_nodes,
                                                  const float4* __restrict__ seg_pts, float qx, float qy, float qz,
                                                  bool active, uint32_t split_mask, Best& b) {
-    NNVisitor v{b, seg_pts, qx, qy, qz};
+    NNVisitor v{b, seg_pts, qx, qy, qz, make_neg_query(qx, qy, qz)};
     wide_traverse_warp(sh, seg_nodes, qx, qy, qz, active, split_mask, v);
 }
 
@@ -397,10 +437,12 @@ struct KnnVisitor {
     bool active;
     __device__ __forceinline__ uint32_t bound_bits() const { return L.bound_bits(); }
     __device__ __forceinline__ void set_active(bool a) { active = a; }   // a bystander must not park candidates
-    __device__ __forceinline__ void leaf(uint32_t g) {
+    __device__ __forceinline__ bool leaf(uint32_t g, bool act) {
         // warp-uniform call; a lane sits out the leaves it has already seen
+        const uint32_t before = L.bound_bits();
         knn_offer_leaf(L, pts, g, qx, qy, qz, active && !(g >= g_lo && g <= g_hi));
         L.maybe_flush(k, pts);
+        return __any_sync(0xffffffffu, act && L.bound_bits() != before);
     }
 };
 

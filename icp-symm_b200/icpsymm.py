@@ -12,14 +12,14 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libicpsymm_b200.so")
+LIB_PATH = os.path.join(_HERE, "libicpsymm_b200.so")   # developer tools point this at an alternative build before load()
 NSUMS = 37
 
 OK, WARN_DEGENERATE = 0, 1
 ERR_INVALID, ERR_CUDA, ERR_NOT_READY, ERR_SIZE, ERR_NONFINITE, ERR_COMM = -1, -2, -3, -4, -5, -6
 OPT_REL_DIFF_TOL, OPT_IDENTITY_PAIRS, OPT_MAX_PAIR_DIST, OPT_USE_GRAPH = 1, 2, 3, 4
 OPT_KERNEL_TIMING, OPT_WARM_START, OPT_TRACE, OPT_GRID_BLOCKS, OPT_ASYNC_SETUP = 5, 6, 7, 8, 9
-OPT_MIN_NORMAL_DOT = 10
+OPT_MIN_NORMAL_DOT, OPT_PEER_TIMEOUT_MS = 10, 11
 
 
 class Stats(C.Structure):

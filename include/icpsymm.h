@@ -67,10 +67,14 @@ enum {
     ICPSYMM_OPT_USE_GRAPH = 4,      /* 1 (default) = CUDA graph with a device-side WHILE node; 2 = unrolled graph
                                        ((max_iters+1) x [search, solve] with early exits); 0 = plain stream launches */
     ICPSYMM_OPT_KERNEL_TIMING = 5,  /* 1 = per-kernel CUDA-event timing (forces stream mode) */
-    ICPSYMM_OPT_WARM_START = 6,     /* 1 (default) = seed each search with the previous correspondence */
+    ICPSYMM_OPT_WARM_START = 6,     /* 1 (default) = seed each search with the previous correspondence; 2 = also seed the
+                                       first search with the correspondences the previous call left for the SAME clouds
+                                       (re-registration from another start; a seed is only a candidate: results stay exact) */
     ICPSYMM_OPT_TRACE = 7,          /* 1 = keep per-search transform + diff (icpsymm_get_trace) */
     ICPSYMM_OPT_GRID_BLOCKS = 8,    /* blocks per pair for the search kernel, 0 = auto */
     ICPSYMM_OPT_MIN_NORMAL_DOT = 10, /* <= -1 = off; reject pairs whose normals disagree: n_p . n_q < value */
+    ICPSYMM_OPT_PEER_TIMEOUT_MS = 11, /* NVLink peer exchange: how long a rank waits for its peers' sums (default 10000 ms)
+                                        before the call fails with ICPSYMM_ERR_COMM */
     ICPSYMM_OPT_ASYNC_SETUP = 9     /* 1 = set_source / set_target / estimate_normals return without waiting: each cloud is
                                        uploaded, indexed and given normals on its own stream, so the upload of one cloud
                                        overlaps the build of the other; a NaN/Inf input is then reported by the next call
@@ -154,7 +158,11 @@ int icpsymm_set_query_shard(icpsymm_ctx* ctx, int rank, int n_ranks); /* without
  * into every peer's exchange buffer over NVLink (CUDA IPC peer mapping), waits for the peers' sums
  * of the same iteration and adds them in rank order -- one kernel, usable inside the device-side
  * loop graph.  Each rank exports a 64-byte handle, the host application gathers the handles of all
- * ranks (any transport) and every rank attaches with the full table.  Single pairs only. */
+ * ranks (any transport) and every rank attaches with the full table.  Single pairs only.
+ * Attach and detach are collective (all ranks, each followed by a host-side barrier of the application before
+ * the first sharded registration); they reset the exchange sequence.  Only icpsymm_register_symm is collective:
+ * the single-search calls (find_correspondences, eval_diff, normal_equations) work on the rank's own shard.
+ * A peer that does not publish within ICPSYMM_OPT_PEER_TIMEOUT_MS fails the call with ICPSYMM_ERR_COMM. */
 int icpsymm_peer_export(icpsymm_ctx* ctx, void* handle64_out);
 int icpsymm_peer_attach(icpsymm_ctx* ctx, const void* handles /* n_ranks x 64 bytes */, int n_ranks, int rank);
 int icpsymm_peer_detach(icpsymm_ctx* ctx);
