@@ -97,7 +97,7 @@ void icpsymm_destroy(icpsymm_ctx* ctx) {
     }
     if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
     cudaFree(ctx->d_state); cudaFree(ctx->d_lp); cudaFree(ctx->d_ctrl);
-    cudaFree(ctx->corr_pos); cudaFree(ctx->partial); cudaFree(ctx->gsum); cudaFree(ctx->trace_T);
+    cudaFree(ctx->corr_pos); cudaFree(ctx->partial); cudaFree(ctx->gsum); cudaFree(ctx->gparts); cudaFree(ctx->trace_T);
     cudaFree(ctx->trace_diff); cudaFree(ctx->io_buf);
     if (ctx->h_state) cudaFreeHost(ctx->h_state);
     if (ctx->ev_begin) cudaEventDestroy(ctx->ev_begin);

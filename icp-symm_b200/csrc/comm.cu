@@ -68,6 +68,7 @@ extern "C" int icpsymm_comm_unique_id(void* id_out128) {
 
 extern "C" int icpsymm_comm_init(icpsymm_ctx* ctx, const void* id128, int n_ranks, int rank) {
     if (!ctx || !id128 || n_ranks < 1 || rank < 0 || rank >= n_ranks) return ICPSYMM_ERR_INVALID;
+    if (n_ranks > ICP_NPARTS) return icp_fail_msg(ctx, ICPSYMM_ERR_INVALID, "query sharding supports at most 8 ranks");
     if (!load_nccl()) return icp_fail_msg(ctx, ICPSYMM_ERR_COMM, "libnccl.so.2 not found");
     if (ctx->nccl_comm) { g_nccl.comm_destroy(ctx->nccl_comm); ctx->nccl_comm = nullptr; }
     if (cudaSetDevice(ctx->device) != cudaSuccess) return icp_fail_msg(ctx, ICPSYMM_ERR_CUDA, "cudaSetDevice");
@@ -96,14 +97,14 @@ extern "C" int icpsymm_comm_destroy(icpsymm_ctx* ctx) {
 }
 
 extern "C" int icpsymm_set_query_shard(icpsymm_ctx* ctx, int rank, int n_ranks) {
-    if (!ctx || n_ranks < 1 || rank < 0 || rank >= n_ranks) return ICPSYMM_ERR_INVALID;
+    if (!ctx || n_ranks < 1 || n_ranks > ICP_NPARTS || rank < 0 || rank >= n_ranks) return ICPSYMM_ERR_INVALID;
     ctx->shard_rank = rank;
     ctx->shard_world = n_ranks;
     return ICPSYMM_OK;
 }
 
 // ---- NVLink peer exchange (used by solve_kernel, icp_loop.cu) ------------------------------------
-static size_t peer_buffer_bytes() { return sizeof(PeerSlot) * 2 * ICP_MAX_PEERS; }
+static size_t peer_buffer_bytes() { return sizeof(PeerBuf); }
 
 extern "C" int icpsymm_peer_export(icpsymm_ctx* ctx, void* handle64_out) {
     if (!ctx || !handle64_out) return ICPSYMM_ERR_INVALID;

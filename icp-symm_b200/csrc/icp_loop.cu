@@ -56,10 +56,7 @@ extern "C" int icpsymm_debug_k1_times(unsigned long long* out, int n) {
 
 namespace {
 
-#ifndef ICP_K1_THREADS
-#define ICP_K1_THREADS 256
-#endif
-constexpr int kNNThreads = ICP_K1_THREADS;
+constexpr int kNNThreads = ICP_TILE;   // one block = one 256-query tile at a time
 constexpr int kNNBlocksPerSM = 1024 / kNNThreads;   // 64 registers per thread: 1024 threads per SM
 constexpr int kNNWarps = kNNThreads / 32;
 #ifndef ICP_K2_THREADS
@@ -76,9 +73,9 @@ struct NNParams {
     SegState* state;
     const LoopParams* lp;
     uint32_t* corr_pos;
-    double* partial;
-    uint32_t blocks_per_seg;
-    int shard_rank, shard_world;
+    double* partial;          // [pair][part][part_blocks] rows of ICP_PART_STRIDE doubles
+    uint32_t part_blocks;     // rows reserved per part = icp_part_blocks(tiles of the largest pair)
+    uint32_t part0, nparts;   // parts of every pair this launch covers: 0, 8 = whole pairs; a query shard = a run of parts
 };
 
 struct SolveParams {
@@ -88,13 +85,15 @@ struct SolveParams {
     SegState* state;
     const LoopParams* lp;
     const double* partial;
-    double* gsum;
+    const uint32_t* src_counts;
+    double* gsum;             // [pair][ICP_PART_STRIDE]: totals of the local parts (single searches)
+    double* gparts;           // [pair][ICP_NPARTS][ICP_PART_STRIDE]: part sums, exchange buffer of the NCCL mode
     float* trace_T;
     double* trace_diff;
-    uint32_t blocks_per_seg;
+    uint32_t part_blocks, part0, nparts;
     int trace_stride;
-    int mode;  // 0 reduce+solve, 1 reduce only (-> gsum), 2 solve from gsum, 3 reduce + record, no solve
-    PeerSlot* peers[ICP_MAX_PEERS];   // NVLink peer mode: exchange buffers of all ranks (mine included)
+    int mode;  // 0 reduce+solve, 1 reduce only (-> gparts), 2 solve from gparts, 3 reduce + record (-> gsum), no solve
+    PeerBuf* peers[ICP_MAX_PEERS];   // NVLink peer mode: exchange buffers of all ranks (mine included)
     int peer_world, peer_rank;
     unsigned long long peer_timeout_ns;
 };
@@ -134,8 +133,12 @@ __global__ void __launch_bounds__(kNNThreads, kNNBlocksPerSM) nn_accum_kernel(co
 #ifdef ICP_BLOCK_TIMES
     K1Timer timer_;
 #endif
-    const uint32_t seg = blockIdx.x / P.blocks_per_seg;
-    const uint32_t blk = blockIdx.x - seg * P.blocks_per_seg;
+    // block -> (pair, block of the part, part); parts interleaved so that the two-tile blocks (lowest
+    // block indices of every part) start first and the one-tile blocks fill the tail of the launch
+    const uint32_t per_seg = P.nparts * P.part_blocks;
+    const uint32_t seg = blockIdx.x / per_seg;
+    const uint32_t rem = blockIdx.x - seg * per_seg;
+    const uint32_t blk = rem / P.nparts, part = P.part0 + (rem - blk * P.nparts);
     const SegState* st = P.state + seg;
     __shared__ float sT[12];
     __shared__ float sO[3];
@@ -151,22 +154,20 @@ __global__ void __launch_bounds__(kNNThreads, kNNBlocksPerSM) nn_accum_kernel(co
 
     const LoopParams lp = *P.lp;
     const uint32_t ns = P.src.counts[seg], nt = P.tgt.counts[seg];
-    uint32_t qlo = 0, qhi = ns;
-    if (P.shard_world > 1) {
-        qlo = (uint32_t)(((unsigned long long)ns * (unsigned)P.shard_rank) / (unsigned)P.shard_world);
-        qhi = (uint32_t)(((unsigned long long)ns * (unsigned)(P.shard_rank + 1)) / (unsigned)P.shard_world);
-    }
+    // canonical tile -> block map of this pair (common.cuh): depends on the pair's own point count only
+    const uint32_t tiles = icp_tiles(ns), own_blocks = icp_part_blocks(tiles);
+    if (blk >= own_blocks) return;   // a smaller pair of a batch uses fewer rows than the grid reserves
+    const uint32_t t_lo = icp_part_tile_lo(tiles, part), t_hi = icp_part_tile_lo(tiles, part + 1u);
     const float4* __restrict__ spts = P.src.pts + (size_t)seg * P.src.shape.pitch;
     const float4* __restrict__ snrm = P.src.nrm + (size_t)seg * P.src.shape.pitch;
     const float4* __restrict__ tpts = P.tgt.pts + (size_t)seg * P.tgt.shape.pitch;
     const float4* __restrict__ tnrm = P.tgt.nrm + (size_t)seg * P.tgt.shape.pitch;
     const WideNode* __restrict__ tbox = P.tgt.nodes + (size_t)seg * P.tgt.shape.nodes_per_seg;
     uint32_t* corr = P.corr_pos + (size_t)seg * P.src.shape.pitch;
-    const uint32_t ntiles = (qhi - qlo + kNNThreads - 1) / kNNThreads;
 
-    for (uint32_t tile = blk; tile < ntiles; tile += P.blocks_per_seg) {
-        const uint32_t i = qlo + tile * kNNThreads + tid;
-        const bool active = i < qhi && nt > 0;
+    for (uint32_t tile = t_lo + blk; tile < t_hi; tile += own_blocks) {
+        const uint32_t i = tile * kNNThreads + tid;
+        const bool active = i < ns && nt > 0;
         float3 p = make_float3(0.f, 0.f, 0.f);
         Best b;
         best_init(b);
@@ -260,7 +261,7 @@ __global__ void __launch_bounds__(kNNThreads, kNNBlocksPerSM) nn_accum_kernel(co
         double s = 0.0;
 #pragma unroll
         for (int w = 0; w < kNNWarps; w++) s += wacc[w][tid];
-        P.partial[((size_t)seg * P.blocks_per_seg + blk) * ICP_PART_STRIDE + tid] = s;
+        P.partial[(((size_t)seg * ICP_NPARTS + part) * P.part_blocks + blk) * ICP_PART_STRIDE + tid] = s;
     }
 #ifdef ICP_BLOCK_TIMES
     timer_.stop();
@@ -446,16 +447,21 @@ __device__ __forceinline__ void loop_ctrl_arrive(const SolveParams& P, bool pair
     }
 }
 
-// A pair with many partial rows (a single large pair) is reduced by a thread-block CLUSTER: one
-// block cannot pull rows out of L2 faster than ~100 GB/s, so the cn blocks of a cluster each add a
-// share of the rows, block 0 collects the cn partial vectors through distributed shared memory in
-// rank order, and goes on alone.  Batches of small pairs launch plain blocks (cluster of 1).
+// Canonical reduction (common.cuh): the rows of a part are added in a fixed order (27 interleaved
+// chains, then the chains in order), then the 8 part sums in part order, starting from +0.0.  A single
+// large pair is reduced by a thread-block CLUSTER of 8 blocks, one part each (one block cannot pull
+// rows out of L2 faster than ~100 GB/s); block 0 collects the part sums through distributed shared
+// memory.  Batches of small pairs launch plain blocks that take the parts in turn.  In the
+// query-sharded modes a rank holds a run of parts and the part sums of the others arrive over NVLink
+// (peer stores, fused here) or through NCCL (between a reduce-only and a solve-only launch); the final
+// sum over the 8 parts is the same expression on every rank and on a single GPU.
 __global__ void __launch_bounds__(kSolveThreads) solve_kernel(const __grid_constant__ SolveParams P) {
     cooperative_groups::cluster_group cluster = cooperative_groups::this_cluster();
     const uint32_t cn = cluster.num_blocks(), cr = cluster.block_rank();
     const uint32_t seg = blockIdx.x / cn;
     SegState* st = P.state + seg;
     __shared__ double sPart[kSolveParts][ICP_NSUMS];
+    __shared__ double sOct[ICP_NPARTS][ICP_NSUMS];   // part sums; indexed by LOCAL part until the exchange
     __shared__ double sS[ICP_NSUMS];
     const int tid = threadIdx.x;
     ICP_K2_STAMP(0);
@@ -466,62 +472,70 @@ __global__ void __launch_bounds__(kSolveThreads) solve_kernel(const __grid_const
     }
     if (P.mode == 2 && cr != 0) return;   // solve-only launch: nothing to add up
     if (P.mode != 2) {
-        const int v = tid % ICP_NSUMS, part = tid / ICP_NSUMS;
-        if (part < kSolveParts) {
-            // part g = cr*27 + p of the cn*27 parts adds rows g, g + 27 cn, g + 54 cn, ... in that order;
-            // ICP_K2_BATCH loads are issued back to back so the (L2-latency) loads overlap instead of
-            // serialising with the adds
-            double s = 0.0;
-            const double* row = P.partial + (size_t)seg * P.blocks_per_seg * ICP_PART_STRIDE + v;
-            const uint32_t step = kSolveParts * cn;
-            uint32_t b = cr * kSolveParts + part;
-            for (; b < P.blocks_per_seg; b += ICP_K2_BATCH * step) {
-                double x[ICP_K2_BATCH];   // rows past the end count as 0.0, which leaves the sum unchanged
+        const uint32_t own_blocks = icp_part_blocks(icp_tiles(P.src_counts[seg]));
+        const int v = tid % ICP_NSUMS, chain = tid / ICP_NSUMS;
+        for (uint32_t ol = cr; ol < P.nparts; ol += cn) {
+            if (chain < kSolveParts) {
+                // chain c adds rows c, c + 27, c + 54, ... in that order; ICP_K2_BATCH loads are issued back to
+                // back so the (L2-latency) loads overlap instead of serialising with the adds
+                double s = 0.0;
+                const double* row = P.partial + ((size_t)seg * ICP_NPARTS + P.part0 + ol) * P.part_blocks * ICP_PART_STRIDE + v;
+                for (uint32_t b = chain; b < own_blocks; b += ICP_K2_BATCH * kSolveParts) {
+                    double x[ICP_K2_BATCH];   // rows past the end count as 0.0, which leaves the sum unchanged
 #pragma unroll
-                for (int u = 0; u < ICP_K2_BATCH; u++)
-                    x[u] = (b + u * step < P.blocks_per_seg) ? row[(size_t)(b + u * step) * ICP_PART_STRIDE] : 0.0;
+                    for (int u = 0; u < ICP_K2_BATCH; u++)
+                        x[u] = (b + u * kSolveParts < own_blocks) ? row[(size_t)(b + u * kSolveParts) * ICP_PART_STRIDE] : 0.0;
 #pragma unroll
-                for (int u = 0; u < ICP_K2_BATCH; u++) s += x[u];
+                    for (int u = 0; u < ICP_K2_BATCH; u++) s += x[u];
+                }
+                sPart[chain][v] = s;
             }
-            sPart[part][v] = s;
-        }
-        __syncthreads();
-        if (tid < ICP_NSUMS) {
-            double s = 0.0;
-            for (int p = 0; p < kSolveParts; p++) s += sPart[p][tid];
-            sS[tid] = s;
+            __syncthreads();
+            if (tid < ICP_NSUMS) {
+                double s = 0.0;
+                for (int p = 0; p < kSolveParts; p++) s += sPart[p][tid];
+                sOct[ol][tid] = s;
+            }
+            __syncthreads();
         }
         ICP_K2_STAMP(1);
         if (cn > 1) {
-            cluster.sync();                         // every block's sS is complete
-            if (cr == 0 && tid < ICP_NSUMS) {
-                double s = sS[tid];
-                for (uint32_t r = 1; r < cn; r++) s += cluster.map_shared_rank(sS, r)[tid];
-                sS[tid] = s;
-            }
+            cluster.sync();                         // block ol holds the sum of local part ol
+            if (cr == 0 && tid < ICP_NSUMS)
+                for (uint32_t ol = 1; ol < P.nparts; ol++)
+                    sOct[ol][tid] = cluster.map_shared_rank(&sOct[0][0], ol % cn)[ol * ICP_NSUMS + tid];
             cluster.sync();                         // block 0 has read: the others may leave
             if (cr != 0) return;
+            __syncthreads();
         }
-        if (tid < ICP_NSUMS && (P.mode == 1 || P.mode == 3)) P.gsum[(size_t)seg * ICP_PART_STRIDE + tid] = sS[tid];
-        __syncthreads();
-        if (P.mode == 1) return;
+        if (P.mode == 1) {
+            // NCCL mode: my parts' sums, zeros for the parts of the other ranks -- the all-reduce then adds
+            // exact zeros to every value, so its result does not depend on NCCL's reduction order
+            for (int t = tid; t < ICP_NPARTS * ICP_PART_STRIDE; t += kSolveThreads) {
+                const uint32_t o = t / ICP_PART_STRIDE, j = t % ICP_PART_STRIDE;
+                const bool mine = o >= P.part0 && o < P.part0 + P.nparts && j < ICP_NSUMS;
+                P.gparts[(size_t)seg * ICP_NPARTS * ICP_PART_STRIDE + t] = mine ? sOct[o - P.part0][j] : 0.0;
+            }
+            return;
+        }
         if (P.peer_world > 1) {
-            // ---- fused exchange over NVLink: store my sums into every rank's buffer, publish, wait
-            // for the same iteration of every peer, add in rank order (bit-identical on all ranks) ----
+            // ---- fused exchange over NVLink: store my part sums into every rank's buffer, publish, wait
+            // for the same exchange of every peer, then read all 8 parts from my own buffer ----
             const unsigned long long seq = P.ctrl->seq + 1ull;
             const int par = (int)(seq & 1ull);
-            if (tid < ICP_PART_STRIDE) {
-                const double v = tid < ICP_NSUMS ? sS[tid] : 0.0;
-                for (int r = 0; r < P.peer_world; r++) P.peers[r][par * ICP_MAX_PEERS + P.peer_rank].sums[tid] = v;
+            if (tid < (int)(P.nparts * ICP_PART_STRIDE)) {
+                const uint32_t ol = tid / ICP_PART_STRIDE, j = tid % ICP_PART_STRIDE;
+                const double val = j < ICP_NSUMS ? sOct[ol][j] : 0.0;
+                for (int r = 0; r < P.peer_world; r++) P.peers[r]->sums[par][P.part0 + ol][j] = val;
                 __threadfence_system();
             }
             __syncthreads();
             if (tid < P.peer_world) {
-                volatile unsigned long long* flag = &P.peers[tid][par * ICP_MAX_PEERS + P.peer_rank].seq;
+                volatile unsigned long long* flag = &P.peers[tid]->flag[par][P.peer_rank].seq;
                 *flag = seq;
                 __threadfence_system();
-                // wait until rank `tid` has published this iteration into MY buffer
-                volatile unsigned long long* mine = &P.peers[P.peer_rank][par * ICP_MAX_PEERS + tid].seq;
+                // wait until rank `tid` has published this exchange into MY buffer
+                volatile unsigned long long* mine = &P.peers[P.peer_rank]->flag[par][tid].seq;
                 unsigned long long t0, t1;
                 asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
                 while (*mine != seq) {   // bounded: a rank that never publishes must not hang the GPU
@@ -532,18 +546,29 @@ __global__ void __launch_bounds__(kSolveThreads) solve_kernel(const __grid_const
             }
             __syncthreads();
             if (tid < ICP_NSUMS) {
+                const volatile double* all = &P.peers[P.peer_rank]->sums[par][0][0];
                 double s = 0.0;
-                for (int r = 0; r < P.peer_world; r++) {
-                    const volatile double* src = P.peers[P.peer_rank][par * ICP_MAX_PEERS + r].sums;
-                    s += src[tid];
-                }
+                for (int o = 0; o < ICP_NPARTS; o++) s += all[o * ICP_PART_STRIDE + tid];
                 sS[tid] = s;
             }
             __syncthreads();
             if (tid == 0) P.ctrl->seq = seq;
+        } else {
+            if (tid < ICP_NSUMS) {
+                double s = 0.0;
+                for (uint32_t ol = 0; ol < P.nparts; ol++) s += sOct[ol][tid];
+                sS[tid] = s;
+            }
+            __syncthreads();
         }
+        if (tid < ICP_NSUMS && P.mode == 3) P.gsum[(size_t)seg * ICP_PART_STRIDE + tid] = sS[tid];
     } else {
-        if (tid < ICP_NSUMS) sS[tid] = P.gsum[(size_t)seg * ICP_PART_STRIDE + tid];
+        if (tid < ICP_NSUMS) {
+            const double* all = P.gparts + (size_t)seg * ICP_NPARTS * ICP_PART_STRIDE;
+            double s = 0.0;
+            for (int o = 0; o < ICP_NPARTS; o++) s += all[o * ICP_PART_STRIDE + tid];
+            sS[tid] = s;
+        }
         __syncthreads();
     }
     if (tid != 0) return;
@@ -654,43 +679,9 @@ static int ensure_io(icpsymm_ctx* ctx, size_t bytes) {
     return rc;
 }
 
-static uint32_t choose_blocks_per_seg(const icpsymm_ctx* ctx, uint32_t nseg, uint32_t max_queries) {
-    uint32_t ntiles = (max_queries + kNNThreads - 1) / kNNThreads;
-    if (ntiles < 1) ntiles = 1;
-    uint32_t bps;
-    if (ctx->opt_grid_blocks > 0) bps = (uint32_t)ctx->opt_grid_blocks;
-    else {
-        const uint32_t resident = (uint32_t)ctx->sm_count * (uint32_t)kNNBlocksPerSM;   // resident blocks
-        uint32_t target = resident * 4u;                          // 4 waves: measured best at 1M and beyond
-        // between one and two tiles per block the blocks with two tiles (lowest indices) start first and
-        // the one-tile blocks fill the tail; about 3/4 of the tile count, rounded to whole waves, balances
-        // best (1M points: 3907 tiles -> 2960 blocks, 5 % faster than 2368)
-        if (nseg == 1 && ntiles > target && ntiles < 2u * target)
-            target = ((ntiles * 3u / 4u + resident - 1u) / resident) * resident;
-        else if (nseg == 1 && ntiles >= 2u * target) {
-            // larger pairs: about 2.2 tiles per block in whole waves, at most 16 waves (4M points:
-            // 7104 blocks, 5 % faster than 2368; the cluster reduction of K2 makes the extra rows cheap)
-            target = ((ntiles * 9u / 20u + resident - 1u) / resident) * resident;
-            if (target > 16u * resident) target = 16u * resident;
-        }
-        bps = (target + nseg - 1) / nseg;
-        if (nseg > 1) {
-            // batches: about 4 tiles per block (256 pairs of 32K points: 32 blocks per pair, 4 % faster than
-            // 10), as long as the grid stays below 32K blocks -- blocks of finished pairs only exit
-            uint32_t want = (ntiles + 3u) / 4u;
-            const uint32_t cap = 32768u / nseg;
-            if (want > cap) want = cap;
-            if (want > bps) bps = want;
-        }
-    }
-    if (bps > ntiles) bps = ntiles;
-    if (bps < 1) bps = 1;
-    return bps;
-}
-
 // one block per pair, or a cluster of 8 blocks per pair when there are many rows and few pairs
 static void launch_solve(const SolveParams& sp, uint32_t nseg, cudaStream_t st) {
-    const unsigned cn = (sp.blocks_per_seg >= 512u && nseg <= 16u) ? 8u : 1u;
+    const unsigned cn = (sp.part_blocks >= 64u && nseg <= 16u) ? 8u : 1u;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(nseg * cn); cfg.blockDim = dim3(kSolveThreads); cfg.dynamicSmemBytes = 0; cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -704,14 +695,14 @@ static void launch_iteration(icpsymm_ctx* ctx, const NNParams& np, SolveParams s
                              cudaEvent_t* ev /*4 events or null*/) {
     cudaStream_t st = ctx->stream;
     if (ev) cudaEventRecord(ev[0], st);
-    nn_accum_kernel<<<nseg * np.blocks_per_seg, kNNThreads, 0, st>>>(np);
+    nn_accum_kernel<<<nseg * np.nparts * np.part_blocks, kNNThreads, 0, st>>>(np);
     if (ev) { cudaEventRecord(ev[1], st); cudaEventRecord(ev[2], st); }
     if (!use_comm) {
         launch_solve(sp, nseg, st);
     } else {
         sp.mode = 1;
         launch_solve(sp, nseg, st);
-        icp_comm_allreduce(ctx, sp.gsum, (size_t)nseg * ICP_PART_STRIDE);
+        icp_comm_allreduce(ctx, sp.gparts, (size_t)nseg * ICP_NPARTS * ICP_PART_STRIDE);
         sp.mode = 2;
         launch_solve(sp, nseg, st);
     }
@@ -736,9 +727,12 @@ int icp_run_loop(icpsymm_ctx* ctx, int max_iters, float thr, const float* T_init
     cudaStream_t st = ctx->stream;
     int rc;
 
-    uint32_t max_q = S.max_count;
-    if (ctx->shard_world > 1) max_q = (uint32_t)((S.max_count + ctx->shard_world - 1) / ctx->shard_world) + 1;
-    const uint32_t bps = choose_blocks_per_seg(ctx, nseg, max_q);
+    // canonical grid (common.cuh): rows per part from the largest pair; a query shard is a run of whole parts
+    if (ctx->shard_world > ICP_NPARTS)
+        return icp_fail_msg(ctx, ICPSYMM_ERR_INVALID, "query sharding supports at most 8 ranks (one NVSwitch domain)");
+    const uint32_t bps = icp_part_blocks(icp_tiles(S.max_count));
+    const uint32_t part0 = (uint32_t)(ICP_NPARTS * ctx->shard_rank / ctx->shard_world);
+    const uint32_t nparts = (uint32_t)(ICP_NPARTS * (ctx->shard_rank + 1) / ctx->shard_world) - part0;
 
     if ((rc = icp_reserve(ctx, &ctx->d_state, &ctx->state_cap, nseg))) return rc;
     if (ctx->h_state_cap < nseg) {
@@ -747,8 +741,9 @@ int icp_run_loop(icpsymm_ctx* ctx, int max_iters, float thr, const float* T_init
         ICP_CUDA_CHECK(cudaMallocHost((void**)&ctx->h_state, sizeof(SegState) * nseg));
         ctx->h_state_cap = nseg;
     }
-    if ((rc = icp_reserve(ctx, &ctx->partial, &ctx->partial_cap, (size_t)nseg * bps * ICP_PART_STRIDE))) return rc;
+    if ((rc = icp_reserve(ctx, &ctx->partial, &ctx->partial_cap, (size_t)nseg * ICP_NPARTS * bps * ICP_PART_STRIDE))) return rc;
     if ((rc = icp_reserve(ctx, &ctx->gsum, &ctx->gsum_cap, (size_t)nseg * ICP_PART_STRIDE))) return rc;
+    if ((rc = icp_reserve(ctx, &ctx->gparts, &ctx->gparts_cap, (size_t)nseg * ICP_NPARTS * ICP_PART_STRIDE))) return rc;
     if ((rc = icp_reserve(ctx, &ctx->corr_pos, &ctx->corr_cap, (size_t)nseg * S.shape.pitch))) return rc;
     if (!ctx->d_lp) ICP_CUDA_CHECK(cudaMalloc((void**)&ctx->d_lp, sizeof(LoopParams)));
     const int n_search = single_search ? 1 : max_iters + 1;
@@ -789,12 +784,13 @@ int icp_run_loop(icpsymm_ctx* ctx, int max_iters, float thr, const float* T_init
     NNParams np;
     np.src = S.view(); np.tgt = T.view();
     np.state = ctx->d_state; np.lp = ctx->d_lp; np.corr_pos = ctx->corr_pos; np.partial = ctx->partial;
-    np.blocks_per_seg = bps; np.shard_rank = ctx->shard_rank; np.shard_world = ctx->shard_world;
+    np.part_blocks = bps; np.part0 = part0; np.nparts = nparts;
     SolveParams sp;
-    sp.state = ctx->d_state; sp.lp = ctx->d_lp; sp.partial = ctx->partial; sp.gsum = ctx->gsum;
+    sp.state = ctx->d_state; sp.lp = ctx->d_lp; sp.partial = ctx->partial; sp.gsum = ctx->gsum; sp.gparts = ctx->gparts;
+    sp.src_counts = S.counts; sp.part_blocks = bps; sp.part0 = part0; sp.nparts = nparts;
     sp.trace_T = ctx->opt_trace ? ctx->trace_T : nullptr;
     sp.trace_diff = ctx->opt_trace ? ctx->trace_diff : nullptr;
-    sp.blocks_per_seg = bps; sp.trace_stride = ctx->trace_stride; sp.mode = single_search ? 3 : 0;
+    sp.trace_stride = ctx->trace_stride; sp.mode = single_search ? 3 : 0;
     if (!ctx->d_ctrl) {
         ICP_CUDA_CHECK(cudaMalloc((void**)&ctx->d_ctrl, sizeof(LoopCtrl)));
         ICP_CUDA_CHECK(cudaMemsetAsync(ctx->d_ctrl, 0, sizeof(LoopCtrl), st));
@@ -804,7 +800,7 @@ int icp_run_loop(icpsymm_ctx* ctx, int max_iters, float thr, const float* T_init
     // the registration loop is collective, so one rank may call them without stalling on its peers
     sp.peer_world = single_search ? 0 : ctx->peer_world; sp.peer_rank = ctx->shard_rank;
     sp.peer_timeout_ns = (unsigned long long)(ctx->opt_peer_timeout_ms * 1e6);
-    for (int r = 0; r < ICP_MAX_PEERS; r++) sp.peers[r] = (PeerSlot*)ctx->peer_ptrs[r];
+    for (int r = 0; r < ICP_MAX_PEERS; r++) sp.peers[r] = (PeerBuf*)ctx->peer_ptrs[r];
     if (ctx->peer_world > 1 && nseg != 1)
         return icp_fail_msg(ctx, ICPSYMM_ERR_INVALID, "the NVLink peer exchange supports single pairs only");
 
@@ -826,7 +822,7 @@ int icp_run_loop(icpsymm_ctx* ctx, int max_iters, float thr, const float* T_init
 
     if (use_graph) {
         GraphKey key;
-        key.max_iters = max_iters; key.nseg = nseg; key.blocks_per_seg = bps;
+        key.max_iters = max_iters; key.nseg = nseg; key.blocks_per_seg = bps;   // the parts follow from the shard
         key.src_pitch = S.shape.pitch; key.tgt_pitch = T.shape.pitch;
         key.generation = ctx->generation;
         key.shard_rank = ctx->shard_rank; key.shard_world = ctx->shard_world; key.trace = ctx->opt_trace;
@@ -918,8 +914,9 @@ int icp_run_loop(icpsymm_ctx* ctx, int max_iters, float thr, const float* T_init
             o.diff = hs.diff;
             uint32_t nq = S.h_counts[s];
             if (ctx->shard_world > 1) {
-                uint32_t lo = (uint32_t)(((unsigned long long)nq * ctx->shard_rank) / ctx->shard_world);
-                uint32_t hi = (uint32_t)(((unsigned long long)nq * (ctx->shard_rank + 1)) / ctx->shard_world);
+                const uint32_t tiles = icp_tiles(nq);
+                uint32_t lo = icp_part_tile_lo(tiles, part0) * ICP_TILE, hi = icp_part_tile_lo(tiles, part0 + nparts) * ICP_TILE;
+                if (hi > nq) hi = nq;
                 nq = (use_comm || (ctx->peer_world > 1 && !single_search)) ? nq : hi - lo;   // global sums: all source points
             }
             o.rmse = nq ? sqrt(hs.sumd2 / (double)nq) : 0.0;

@@ -87,6 +87,7 @@ struct icpsymm_ctx {
     uint32_t* corr_pos = nullptr; size_t corr_cap = 0;
     double* partial = nullptr;    size_t partial_cap = 0;
     double* gsum = nullptr;       size_t gsum_cap = 0;
+    double* gparts = nullptr;     size_t gparts_cap = 0;   // part sums: exchange buffer of the NCCL mode
     float* trace_T = nullptr;     size_t trace_T_cap = 0;      // floats
     double* trace_diff = nullptr; size_t trace_diff_cap = 0;   // doubles
     int trace_stride = 0;

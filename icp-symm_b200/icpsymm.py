@@ -326,6 +326,12 @@ class Context:
         buf = C.create_string_buffer(handles, 64 * world)
         self._check(self.L.icpsymm_peer_attach(self.h, buf, world, rank))
 
+    def peer_detach(self):
+        self._check(self.L.icpsymm_peer_detach(self.h))
+
+    def comm_destroy(self):
+        self._check(self.L.icpsymm_comm_destroy(self.h))
+
     def comm_init(self, unique_id: bytes, world, rank):
         buf = C.create_string_buffer(unique_id, 128)
         self._check(self.L.icpsymm_comm_init(self.h, buf, world, rank))

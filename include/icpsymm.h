@@ -71,7 +71,8 @@ enum {
                                        first search with the correspondences the previous call left for the SAME clouds
                                        (re-registration from another start; a seed is only a candidate: results stay exact) */
     ICPSYMM_OPT_TRACE = 7,          /* 1 = keep per-search transform + diff (icpsymm_get_trace) */
-    ICPSYMM_OPT_GRID_BLOCKS = 8,    /* blocks per pair for the search kernel, 0 = auto */
+    ICPSYMM_OPT_GRID_BLOCKS = 8,    /* accepted and ignored: the tile -> block map of the search kernel is canonical (a function
+                                       of the pair's point count only), which is what makes results independent of the GPU count */
     ICPSYMM_OPT_MIN_NORMAL_DOT = 10, /* <= -1 = off; reject pairs whose normals disagree: n_p . n_q < value */
     ICPSYMM_OPT_PEER_TIMEOUT_MS = 11, /* NVLink peer exchange: how long a rank waits for its peers' sums (default 10000 ms)
                                         before the call fails with ICPSYMM_ERR_COMM */
@@ -148,8 +149,11 @@ int icpsymm_register_npoint(icpsymm_ctx* ctx, const double* src_xyz, const doubl
                             double R[9], double T[3]);
 
 /* ---- multi-GPU.  Pair batches need nothing: each rank registers its own pairs.
- * Query sharding: every rank holds the full clouds; rank r searches the r-th slice of the sorted
- * source and the 37-value normal equations are summed across ranks before the solve. ---- */
+ * Query sharding: every rank holds the full clouds; rank r of n_ranks <= 8 searches its slice of the sorted
+ * source and the 37-value normal equations are summed across ranks before the solve.  The sums have a
+ * canonical order (8 fixed parts of the source, a shard is a run of whole parts), so the
+ * transform, the iteration count and the correspondences are BIT-IDENTICAL for 1, 2, 4 and 8 ranks and for
+ * both exchange mechanisms below. ---- */
 int icpsymm_comm_unique_id(void* id_out128);                       /* ncclGetUniqueId on the root */
 int icpsymm_comm_init(icpsymm_ctx* ctx, const void* id128, int n_ranks, int rank);
 int icpsymm_comm_destroy(icpsymm_ctx* ctx);

@@ -371,6 +371,42 @@ def test_query_shards_sum_to_whole(ctx, cat, cat_out):
         ctx.set_query_shard(0, 1)
         assert np.array_equal(idx, idx_whole)
         assert np.allclose(np.sum(parts, axis=0), whole, rtol=1e-5, atol=1e-6 * np.abs(whole).max())  # fp32 reassociation
+    # canonical order (csrc/common.cuh): 8 ranks own one part each, and the whole is the 8 part sums added in
+    # part order starting from +0.0 -- the very expression every rank evaluates after the exchange
+    parts = []
+    for r in range(8):
+        ctx.set_query_shard(r, 8)
+        parts.append(ctx.normal_equations(None, (0, 0, 0)))
+    ctx.set_query_shard(0, 1)
+    acc = np.zeros(icp.NSUMS)
+    for prt in parts:
+        acc = acc + prt
+    assert np.array_equal(acc, whole)
+    with pytest.raises(icp.IcpError):
+        ctx.set_query_shard(0, 9)
+
+
+def test_result_does_not_depend_on_the_batch_a_pair_sits_in(ctx):
+    """the tile -> block map and the order of the sums follow from the pair's own point count: a pair gives the
+    same bits alone, as the small member of a ragged batch, and next to a much larger pair"""
+    pairs = [wl.config_batch_pair(b, n) for b, n in ((0, 20000), (1, 70000), (2, 3000))]
+    res = []
+    for s, t, _ in pairs:
+        ctx.set_source(s); ctx.set_target(t); ctx.estimate_normals(10)
+        T1, st1, _ = ctx.register_symm(30, 1e-3)
+        res.append((T1.copy(), st1, ctx.get_correspondences()[0].copy()))
+    m = max(len(p[0]) for p in pairs)
+    S = np.zeros((3, m, 3), np.float32); Tg = np.zeros((3, m, 3), np.float32)
+    counts = np.array([len(p[0]) for p in pairs], np.uint32)
+    for b, (s, t, _) in enumerate(pairs):
+        S[b, :len(s)], Tg[b, :len(t)] = s, t
+    ctx.set_source_batch(S, counts); ctx.set_target_batch(Tg, counts); ctx.estimate_normals(10)
+    Tb, stb, _ = ctx.register_symm(30, 1e-3)
+    idxb = ctx.get_correspondences()[0].reshape(3, m)
+    for b in range(3):
+        assert np.array_equal(Tb[b], res[b][0]), b
+        assert stb[b]["iters"] == res[b][1]["iters"] and stb[b]["diff"] == res[b][1]["diff"]
+        assert np.array_equal(idxb[b, :counts[b]], res[b][2])
 
 
 def test_register_npoint_regist_h(ctx, cat, cat_out, gold):
