@@ -98,7 +98,7 @@ void icpsymm_destroy(icpsymm_ctx* ctx) {
     if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
     cudaFree(ctx->d_state); cudaFree(ctx->d_lp); cudaFree(ctx->d_ctrl);
     cudaFree(ctx->corr_pos); cudaFree(ctx->partial); cudaFree(ctx->gsum); cudaFree(ctx->gparts); cudaFree(ctx->trace_T);
-    cudaFree(ctx->trace_diff); cudaFree(ctx->io_buf);
+    cudaFree(ctx->trace_diff); cudaFree(ctx->io_buf); cudaFree(ctx->order_buf); cudaFree(ctx->order_temp);
     if (ctx->h_state) cudaFreeHost(ctx->h_state);
     if (ctx->ev_begin) cudaEventDestroy(ctx->ev_begin);
     if (ctx->ev_end) cudaEventDestroy(ctx->ev_end);
@@ -130,6 +130,7 @@ int icpsymm_set_option(icpsymm_ctx* ctx, int key, double value) {
         case ICPSYMM_OPT_WARM_START: ctx->opt_warm_start = (value == 2) ? 2 : (value != 0); break;
         case ICPSYMM_OPT_TRACE: ctx->opt_trace = value != 0; break;
         case ICPSYMM_OPT_GRID_BLOCKS: if (value < 0) return ICPSYMM_ERR_INVALID; ctx->opt_grid_blocks = (int)value; break;
+        case ICPSYMM_OPT_TILE_ORDER: ctx->opt_tile_order = value != 0; break;
         case ICPSYMM_OPT_ASYNC_SETUP: {
             int jr = icp_join_clouds(ctx, true);   // never switch modes with work in flight
             ctx->opt_async_setup = value != 0;
@@ -255,6 +256,11 @@ int icpsymm_get_trace(icpsymm_ctx* ctx, size_t pair, int k, float T[16], double*
     }
     if (diff) *diff = d;
     return ICPSYMM_OK;
+}
+
+int icpsymm_get_search_times(icpsymm_ctx* ctx, float* search_ms, float* solve_ms, int n) {
+    if (!ctx || n < 0) return ICPSYMM_ERR_INVALID;
+    return icp_search_times(ctx, search_ms, solve_ms, n);
 }
 
 int icpsymm_register_npoint(icpsymm_ctx* ctx, const double* src, const double* dst, size_t n, double R[9], double T[3]) {

@@ -35,28 +35,17 @@
 
 // ---- canonical order of the normal-equation sums -------------------------------------------------
 // The queries of a pair are cut into 256-point tiles and the tiles into ICP_NPARTS contiguous parts; part
-// o owns tiles [T*o/8, T*(o+1)/8), T = ceil(n/256).  K1 spreads the tiles of a part over icp_part_blocks(T)
-// blocks (tile t0+b, t0+b+B, ... for block b), every block leaves one fp64 row, K2 adds the rows of a
-// part in a fixed order and then the 8 part sums in part order.  Every step depends on the pair's own
-// point count only -- not on the grid, the batch the pair sits in, or the number of GPUs: a query shard
-// is a run of whole parts (rank r of W owns parts [8r/W, 8(r+1)/W)), so a pair registered on 1, 2, 4 or
-// 8 GPUs, alone or inside a batch, gives bit-identical sums, transforms and correspondences.
+// o owns tiles [T*o/8, T*(o+1)/8), T = ceil(n/256).  K1 leaves one fp64 row per TILE (whichever block drew
+// the tile), K2 adds the rows of a part in a fixed order and then the 8 part sums in part order.  Every
+// step depends on the pair's own point count only -- not on the grid, the batch the pair sits in, the
+// scheduling of the tiles or the number of GPUs: a query shard is a run of whole parts (rank r of W owns
+// parts [8r/W, 8(r+1)/W)), so a pair registered on 1, 2, 4 or 8 GPUs, alone or inside a batch, gives
+// bit-identical sums, transforms and correspondences.
 #define ICP_NPARTS 8
 #define ICP_TILE 256                     // queries per tile = threads of a K1 block
 __host__ __device__ __forceinline__ uint32_t icp_tiles(uint32_t n) { return (n + ICP_TILE - 1u) / ICP_TILE; }
 __host__ __device__ __forceinline__ uint32_t icp_part_tile_lo(uint32_t tiles, uint32_t part) {
     return (uint32_t)(((unsigned long long)tiles * part) / ICP_NPARTS);
-}
-// blocks per part: a monotone function of the tile count alone.  Pairs up to 32K points (batches): 2 tiles per block;
-// around 1M points: 4/3 tiles per block (the two-tile blocks start first, the one-tile blocks fill the tail);
-// large pairs: 20/9 tiles per block.
-__host__ __device__ __forceinline__ uint32_t icp_part_blocks(uint32_t tiles) {
-    const uint32_t to = (tiles + ICP_NPARTS - 1u) / ICP_NPARTS;   // tiles of the largest part
-    if (to <= 16u) return to > 1u ? (to + 1u) / 2u : 1u;
-    uint32_t a = (3u * to + 3u) / 4u;
-    if (a > 888u) a = 888u;
-    const uint32_t b = (9u * to + 19u) / 20u;
-    return a > b ? a : b;
 }
 
 // exchange buffer of the NVLink peer mode (one per rank, mapped by every peer): the owner of part o
@@ -77,7 +66,7 @@ struct LoopCtrl {
     unsigned int done_count;  // pairs that are finished (now or earlier) in this iteration
     unsigned long long seq;   // number of peer exchanges done so far (identical on every rank)
     int comm_error;           // a peer did not answer in time
-    int pad;
+    unsigned int work;        // next tile ticket of the running K1 launch (rewound by K2)
 };
 
 // boxes of the 8 children of one internal node, structure-of-arrays so that one node is 12

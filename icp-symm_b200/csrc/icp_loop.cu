@@ -22,6 +22,7 @@
 #include <cstdio>
 #include <cstring>
 #include <cooperative_groups.h>
+#include <cub/device/device_radix_sort.cuh>
 
 #include "internal.h"
 #include "search.cuh"
@@ -54,10 +55,22 @@ extern "C" int icpsymm_debug_k1_times(unsigned long long* out, int n) {
 #define ICP_K2_STAMP(i) do { } while (0)
 #endif
 
+#ifdef ICP_TILE_TIMES   // developer instrumentation: start/end of every tile of the last K1 launch
+__device__ unsigned long long icp_tile_times[2 * 65536];
+extern "C" int icpsymm_debug_tile_times(unsigned long long* out, int n) {
+    cudaDeviceSynchronize();
+    return (int)cudaMemcpyFromSymbol(out, icp_tile_times, sizeof(unsigned long long) * 2 * n);
+}
+#endif
+
 namespace {
 
 constexpr int kNNThreads = ICP_TILE;   // one block = one 256-query tile at a time
 constexpr int kNNBlocksPerSM = 1024 / kNNThreads;   // 64 registers per thread: 1024 threads per SM
+#ifndef ICP_TILES_PER_TICKET
+#define ICP_TILES_PER_TICKET 1
+#endif
+constexpr int kTilesPerTicket = ICP_TILES_PER_TICKET;
 constexpr int kNNWarps = kNNThreads / 32;
 #ifndef ICP_K2_THREADS
 #define ICP_K2_THREADS 1024
@@ -73,9 +86,14 @@ struct NNParams {
     SegState* state;
     const LoopParams* lp;
     uint32_t* corr_pos;
-    double* partial;          // [pair][part][part_blocks] rows of ICP_PART_STRIDE doubles
-    uint32_t part_blocks;     // rows reserved per part = icp_part_blocks(tiles of the largest pair)
+    double* partial;          // [pair][tiles_max] rows of ICP_PART_STRIDE doubles: one row per 256-query tile
+    LoopCtrl* ctrl;           // ticket counter of the dynamic tile hand-out
+    const uint32_t* order;    // ticket -> work item (null: identity)
+    uint32_t tiles_max;       // rows reserved per pair = icp_tiles(largest pair)
     uint32_t part0, nparts;   // parts of every pair this launch covers: 0, 8 = whole pairs; a query shard = a run of parts
+    uint32_t work_per_seg;    // tile slots per pair handed out by this launch (the parts' tile range of the largest pair)
+    uint32_t total_work;      // pairs x work_per_seg
+    uint32_t grid;            // persistent blocks of the launch
 };
 
 struct SolveParams {
@@ -90,7 +108,7 @@ struct SolveParams {
     double* gparts;           // [pair][ICP_NPARTS][ICP_PART_STRIDE]: part sums, exchange buffer of the NCCL mode
     float* trace_T;
     double* trace_diff;
-    uint32_t part_blocks, part0, nparts;
+    uint32_t tiles_max, part0, nparts, k1_grid;
     int trace_stride;
     int mode;  // 0 reduce+solve, 1 reduce only (-> gparts), 2 solve from gparts, 3 reduce + record (-> gsum), no solve
     PeerBuf* peers[ICP_MAX_PEERS];   // NVLink peer mode: exchange buffers of all ranks (mine included)
@@ -107,8 +125,9 @@ struct InitArgs {
 __global__ void set_lp_kernel(LoopParams* dst, LoopParams v) { *dst = v; }
 
 __global__ void init_state_kernel(SegState* state, uint32_t nseg, InitArgs a, const float4* __restrict__ bb_lo,
-                                  const float4* __restrict__ bb_hi) {
+                                  const float4* __restrict__ bb_hi, LoopCtrl* ctrl, uint32_t k1_grid) {
     uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s == 0) ctrl->work = k1_grid;   // tickets below the grid size are implicit
     if (s >= nseg) return;
     SegState st;
     memset(&st, 0, sizeof st);
@@ -127,45 +146,128 @@ __global__ void init_state_kernel(SegState* state, uint32_t nseg, InitArgs a, co
 }
 
 // ------------------------------------------------------------------------------------------------
+// Tile order of the first search.  The cost of an exact search is set by how much of the target lies
+// near the query's ball: a patch close to the medial axis of the target (inside a bulge, 30 degrees off)
+// sees hundreds of candidate boxes at almost the same distance and takes 10-20x longer than a patch just
+// off the surface (measured: median tile 126 us, worst 930 us in a 1.5 ms launch).  With tiles handed out
+// in curve order such tiles start whenever the curve reaches them and the launch ends with a long tail.
+// One warp per tile estimates the cost up front -- r = an upper bound of the NN distance of the tile's
+// middle query (min over the boxes of one coarse level of the distance to the farthest corner), cost =
+// the number of boxes of that level within r -- and the tiles are handed out most expensive first
+// (stable radix sort: equal costs keep curve order, so neighbouring blocks still share lines).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) tile_cost_kernel(CloudView src, CloudView tgt, const SegState* __restrict__ state,
+                                                        uint32_t part0, uint32_t nparts, uint32_t work, int rec_level,
+                                                        uint32_t* __restrict__ key_out, uint32_t* __restrict__ val_out) {
+    const uint32_t wid = (blockIdx.x * 256u + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
+    if (wid >= work) return;
+    const uint32_t ns = src.counts[0], tiles = icp_tiles(ns);
+    const uint32_t tile = icp_part_tile_lo(tiles, part0) + wid;
+    uint32_t cost = 0u;
+    if (tile < icp_part_tile_lo(tiles, part0 + nparts) && tgt.counts[0] > 0) {
+        uint32_t i = tile * ICP_TILE + ICP_TILE / 2;
+        if (i >= ns) i = ns - 1;
+        const float4 sp = ldg4(src.pts + i);
+        const float3 q = apply_rn(state[0].Tf, sp.x, sp.y, sp.z);
+        const WideNode* recs = tgt.nodes + tgt.shape.level_off[rec_level];
+        const uint32_t nbox = tgt.shape.level_cnt[rec_level] * ICP_FAN;
+        float r2 = __int_as_float(0x7f800000);
+        for (uint32_t b = lane; b < nbox; b += 32u) {
+            const WideNode* nd = recs + (b >> ICP_LOG_FAN);
+            const int c = b & (ICP_FAN - 1);
+            const float lx = nd->lox[c], ly = nd->loy[c], lz = nd->loz[c], hx = nd->hix[c], hy = nd->hiy[c], hz = nd->hiz[c];
+            if (lx <= hx) {   // not a padding box
+                const float fx = fmaxf(fabsf(q.x - lx), fabsf(q.x - hx)), fy = fmaxf(fabsf(q.y - ly), fabsf(q.y - hy));
+                const float fz = fmaxf(fabsf(q.z - lz), fabsf(q.z - hz));
+                r2 = fminf(r2, fx * fx + fy * fy + fz * fz);
+            }
+        }
+        r2 = warp_min_f(r2);
+        for (uint32_t b = lane; b < nbox; b += 32u) {
+            const WideNode* nd = recs + (b >> ICP_LOG_FAN);
+            const int c = b & (ICP_FAN - 1);
+            const float lx = nd->lox[c], ly = nd->loy[c], lz = nd->loz[c], hx = nd->hix[c], hy = nd->hiy[c], hz = nd->hiz[c];
+            const float ex = fmaxf(fmaxf(lx - q.x, q.x - hx), 0.f), ey = fmaxf(fmaxf(ly - q.y, q.y - hy), 0.f);
+            const float ez = fmaxf(fmaxf(lz - q.z, q.z - hz), 0.f);
+            cost += (lx <= hx && ex * ex + ey * ey + ez * ez <= r2) ? 1u : 0u;
+        }
+        cost = __reduce_add_sync(0xffffffffu, cost);
+    }
+    if (lane == 0) {
+        key_out[wid] = 0xffffu - (cost > 0xffffu ? 0xffffu : cost);   // ascending key = descending cost
+        val_out[wid] = wid;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // K1: search + accumulate
 // ------------------------------------------------------------------------------------------------
+// Persistent blocks (4 per SM) draw 256-query tiles from a global ticket counter; ticket k is tile
+// order[k] (most expensive first, see tile_cost_kernel) or simply tile k.  The 8 warps of a block always
+// work on the SAME tile: they share its node records and leaf lines in L1, which is worth more than
+// letting them run apart (measured: warps decoupled over the block's tiles +20 % time).  An SM that drew
+// cheap tiles draws more of them -- the cost of a far search varies 3-5x over a cloud.  Which block
+// handles a tile does not touch the result: every tile leaves its own fp64 row (the 8 warps' fp32 shuffle
+// totals added in warp order), and K2 adds the rows in a fixed order (common.cuh).
 __global__ void __launch_bounds__(kNNThreads, kNNBlocksPerSM) nn_accum_kernel(const __grid_constant__ NNParams P) {
 #ifdef ICP_BLOCK_TIMES
     K1Timer timer_;
 #endif
-    // block -> (pair, block of the part, part); parts interleaved so that the two-tile blocks (lowest
-    // block indices of every part) start first and the one-tile blocks fill the tail of the launch
-    const uint32_t per_seg = P.nparts * P.part_blocks;
-    const uint32_t seg = blockIdx.x / per_seg;
-    const uint32_t rem = blockIdx.x - seg * per_seg;
-    const uint32_t blk = rem / P.nparts, part = P.part0 + (rem - blk * P.nparts);
-    const SegState* st = P.state + seg;
     __shared__ float sT[12];
     __shared__ float sO[3];
-    __shared__ double wacc[kNNWarps][ICP_NSUMS];
+    // the warps' fp32 totals; double-buffered by ticket parity: one barrier per ticket.  Kept small on purpose: shared
+    // memory comes out of the SM's L1 (4 blocks x this), and the walk lives on its L1 hit rate
+    __shared__ float wacc[2][kTilesPerTicket][kNNWarps][ICP_PART_STRIDE];
     __shared__ int sDone;
+    __shared__ uint32_t sWork[2];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) sDone = st->done;
-    if (tid < 12) sT[tid] = st->Tf[tid];
-    if (tid < 3) sO[tid] = (float)st->origin[tid];
-    for (int v = tid; v < kNNWarps * ICP_NSUMS; v += kNNThreads) (&wacc[0][0])[v] = 0.0;
-    __syncthreads();
-    if (sDone) return;
-
     const LoopParams lp = *P.lp;
-    const uint32_t ns = P.src.counts[seg], nt = P.tgt.counts[seg];
-    // canonical tile -> block map of this pair (common.cuh): depends on the pair's own point count only
-    const uint32_t tiles = icp_tiles(ns), own_blocks = icp_part_blocks(tiles);
-    if (blk >= own_blocks) return;   // a smaller pair of a batch uses fewer rows than the grid reserves
-    const uint32_t t_lo = icp_part_tile_lo(tiles, part), t_hi = icp_part_tile_lo(tiles, part + 1u);
-    const float4* __restrict__ spts = P.src.pts + (size_t)seg * P.src.shape.pitch;
-    const float4* __restrict__ snrm = P.src.nrm + (size_t)seg * P.src.shape.pitch;
-    const float4* __restrict__ tpts = P.tgt.pts + (size_t)seg * P.tgt.shape.pitch;
-    const float4* __restrict__ tnrm = P.tgt.nrm + (size_t)seg * P.tgt.shape.pitch;
-    const WideNode* __restrict__ tbox = P.tgt.nodes + (size_t)seg * P.tgt.shape.nodes_per_seg;
-    uint32_t* corr = P.corr_pos + (size_t)seg * P.src.shape.pitch;
+    uint32_t cur_seg = 0xffffffffu;
+    // tickets 0 .. gridDim-1 are implicit (the counter starts at gridDim); the ticket of the NEXT tile is drawn
+    // at the start of the current one, so the latency of the atomic hides behind the tile's work
+    uint32_t w = blockIdx.x;
+    const bool use_order = P.order != nullptr && P.state[0].searches == 0;   // the order is made for the first search
+    // a ticket is one tile in the ordered first search (fine grain: its tiles differ 20x in cost) and two
+    // neighbouring tiles otherwise: a warp then takes its unit of the first and of the second tile without a
+    // barrier in between, which halves the time warps wait for the slowest of the eight
+    const uint32_t tpt = use_order ? 1u : (uint32_t)kTilesPerTicket;
+    const uint32_t tickets_per_seg = (P.work_per_seg + tpt - 1u) / tpt;
+    const uint32_t total_tickets = (P.total_work / P.work_per_seg) * tickets_per_seg;
+    for (uint32_t it = 0; w < total_tickets; it++) {
+        uint32_t wnext = 0u;
+        if (tid == 0) wnext = atomicAdd(&P.ctrl->work, 1u);
+        const uint32_t we = use_order ? __ldg(P.order + w) : w;
+        const uint32_t seg = we / tickets_per_seg;
+        if (seg != cur_seg) {   // block-uniform: (re)load the pair's transform and origin
+            const SegState* st = P.state + seg;
+            if (tid == 0) sDone = st->done;
+            if (tid < 12) sT[tid] = st->Tf[tid];
+            if (tid < 3) sO[tid] = (float)st->origin[tid];
+            __syncthreads();
+            cur_seg = seg;
+        }
+        const uint32_t ns = P.src.counts[seg], nt = P.tgt.counts[seg];
+        const uint32_t tiles = icp_tiles(ns);
+        const uint32_t tile0 = icp_part_tile_lo(tiles, P.part0) + (we - seg * tickets_per_seg) * tpt;
+        const uint32_t tile_end = icp_part_tile_lo(tiles, P.part0 + P.nparts);
+#ifdef ICP_TILE_TIMES
+        unsigned long long tt0;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt0));
+#endif
+#pragma unroll 1
+        for (uint32_t sub = 0; sub < tpt; sub++) {
+        const uint32_t tile = tile0 + sub;
+        // block-uniform; a finished pair has nothing to do and a smaller pair of a batch has fewer tiles
+        const bool valid = !sDone && tile < tile_end;
+        float (*acc)[ICP_PART_STRIDE] = wacc[it & 1u][sub];
+        if (valid) {
+        const float4* __restrict__ spts = P.src.pts + (size_t)seg * P.src.shape.pitch;
+        const float4* __restrict__ snrm = P.src.nrm + (size_t)seg * P.src.shape.pitch;
+        const float4* __restrict__ tpts = P.tgt.pts + (size_t)seg * P.tgt.shape.pitch;
+        const float4* __restrict__ tnrm = P.tgt.nrm + (size_t)seg * P.tgt.shape.pitch;
+        const WideNode* __restrict__ tbox = P.tgt.nodes + (size_t)seg * P.tgt.shape.nodes_per_seg;
+        uint32_t* corr = P.corr_pos + (size_t)seg * P.src.shape.pitch;
 
-    for (uint32_t tile = t_lo + blk; tile < t_hi; tile += own_blocks) {
         const uint32_t i = tile * kNNThreads + tid;
         const bool active = i < ns && nt > 0;
         float3 p = make_float3(0.f, 0.f, 0.f);
@@ -252,16 +354,30 @@ __global__ void __launch_bounds__(kNNThreads, kNNBlocksPerSM) nn_accum_kernel(co
         }
         v[32] += __shfl_xor_sync(0xffffffffu, v[32], 2);
         v[32] += __shfl_xor_sync(0xffffffffu, v[32], 1);
-        // every lane adds its own total (fp64, this warp's accumulator row)
-        wacc[warp][lane] += (double)v[0];
-        if ((lane & 3) == 0 && 32 + (lane >> 2) < ICP_NSUMS) wacc[warp][32 + (lane >> 2)] += (double)v[32];
-    }
-    __syncthreads();
-    if (tid < ICP_NSUMS) {
-        double s = 0.0;
+        // every lane leaves its own total; the tile's row = the 8 warp totals added in warp order (fp64)
+        acc[warp][lane] = v[0];
+        if ((lane & 3) == 0) acc[warp][32 + (lane >> 2)] = v[32];
+        }   // valid
+        }   // sub
+        if (tid == 0) sWork[it & 1u] = wnext;
+        __syncthreads();
+        if (!sDone && tid < (int)(tpt * ICP_PART_STRIDE)) {
+            const uint32_t sub = tid / ICP_PART_STRIDE, vi = tid - sub * ICP_PART_STRIDE, tile = tile0 + sub;
+            if (vi < ICP_NSUMS && tile < tile_end) {
+                double s = 0.0;
 #pragma unroll
-        for (int w = 0; w < kNNWarps; w++) s += wacc[w][tid];
-        P.partial[(((size_t)seg * ICP_NPARTS + part) * P.part_blocks + blk) * ICP_PART_STRIDE + tid] = s;
+                for (int ww = 0; ww < kNNWarps; ww++) s += (double)wacc[it & 1u][sub][ww][vi];
+                P.partial[((size_t)seg * P.tiles_max + tile) * ICP_PART_STRIDE + vi] = s;
+            }
+        }
+#ifdef ICP_TILE_TIMES
+        if (tid == 0 && tile0 < 65536u) {
+            unsigned long long tt1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt1));
+            icp_tile_times[2 * tile0] = tt0; icp_tile_times[2 * tile0 + 1] = tt1;
+        }
+#endif
+        w = sWork[it & 1u];
     }
 #ifdef ICP_BLOCK_TIMES
     timer_.stop();
@@ -465,6 +581,7 @@ __global__ void __launch_bounds__(kSolveThreads) solve_kernel(const __grid_const
     __shared__ double sS[ICP_NSUMS];
     const int tid = threadIdx.x;
     ICP_K2_STAMP(0);
+    if (blockIdx.x == 0 && tid == 0) P.ctrl->work = P.k1_grid;   // K1 of this iteration is complete: rewind its ticket counter
     if (st->searches == 0) ICP_K2_STAMP(5);
     if (st->done) {   // the same for every block of the cluster: all leave, nobody waits
         if (tid == 0 && cr == 0) loop_ctrl_arrive(P, true);
@@ -472,14 +589,16 @@ __global__ void __launch_bounds__(kSolveThreads) solve_kernel(const __grid_const
     }
     if (P.mode == 2 && cr != 0) return;   // solve-only launch: nothing to add up
     if (P.mode != 2) {
-        const uint32_t own_blocks = icp_part_blocks(icp_tiles(P.src_counts[seg]));
+        const uint32_t tiles = icp_tiles(P.src_counts[seg]);
         const int v = tid % ICP_NSUMS, chain = tid / ICP_NSUMS;
         for (uint32_t ol = cr; ol < P.nparts; ol += cn) {
             if (chain < kSolveParts) {
-                // chain c adds rows c, c + 27, c + 54, ... in that order; ICP_K2_BATCH loads are issued back to
-                // back so the (L2-latency) loads overlap instead of serialising with the adds
+                // chain c adds the part's tile rows c, c + 27, c + 54, ... in that order; ICP_K2_BATCH loads are
+                // issued back to back so the (L2-latency) loads overlap instead of serialising with the adds
                 double s = 0.0;
-                const double* row = P.partial + ((size_t)seg * ICP_NPARTS + P.part0 + ol) * P.part_blocks * ICP_PART_STRIDE + v;
+                const uint32_t t_lo = icp_part_tile_lo(tiles, P.part0 + ol);
+                const uint32_t own_blocks = icp_part_tile_lo(tiles, P.part0 + ol + 1u) - t_lo;   // rows of this part
+                const double* row = P.partial + ((size_t)seg * P.tiles_max + t_lo) * ICP_PART_STRIDE + v;
                 for (uint32_t b = chain; b < own_blocks; b += ICP_K2_BATCH * kSolveParts) {
                     double x[ICP_K2_BATCH];   // rows past the end count as 0.0, which leaves the sum unchanged
 #pragma unroll
@@ -681,7 +800,7 @@ static int ensure_io(icpsymm_ctx* ctx, size_t bytes) {
 
 // one block per pair, or a cluster of 8 blocks per pair when there are many rows and few pairs
 static void launch_solve(const SolveParams& sp, uint32_t nseg, cudaStream_t st) {
-    const unsigned cn = (sp.part_blocks >= 64u && nseg <= 16u) ? 8u : 1u;
+    const unsigned cn = (sp.tiles_max >= 512u && nseg <= 16u) ? 8u : 1u;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(nseg * cn); cfg.blockDim = dim3(kSolveThreads); cfg.dynamicSmemBytes = 0; cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -695,7 +814,7 @@ static void launch_iteration(icpsymm_ctx* ctx, const NNParams& np, SolveParams s
                              cudaEvent_t* ev /*4 events or null*/) {
     cudaStream_t st = ctx->stream;
     if (ev) cudaEventRecord(ev[0], st);
-    nn_accum_kernel<<<nseg * np.nparts * np.part_blocks, kNNThreads, 0, st>>>(np);
+    nn_accum_kernel<<<np.grid, kNNThreads, 0, st>>>(np);
     if (ev) { cudaEventRecord(ev[1], st); cudaEventRecord(ev[2], st); }
     if (!use_comm) {
         launch_solve(sp, nseg, st);
@@ -730,7 +849,7 @@ int icp_run_loop(icpsymm_ctx* ctx, int max_iters, float thr, const float* T_init
     // canonical grid (common.cuh): rows per part from the largest pair; a query shard is a run of whole parts
     if (ctx->shard_world > ICP_NPARTS)
         return icp_fail_msg(ctx, ICPSYMM_ERR_INVALID, "query sharding supports at most 8 ranks (one NVSwitch domain)");
-    const uint32_t bps = icp_part_blocks(icp_tiles(S.max_count));
+    const uint32_t bps = icp_tiles(S.max_count);   // rows per pair: one per tile
     const uint32_t part0 = (uint32_t)(ICP_NPARTS * ctx->shard_rank / ctx->shard_world);
     const uint32_t nparts = (uint32_t)(ICP_NPARTS * (ctx->shard_rank + 1) / ctx->shard_world) - part0;
 
@@ -741,7 +860,7 @@ int icp_run_loop(icpsymm_ctx* ctx, int max_iters, float thr, const float* T_init
         ICP_CUDA_CHECK(cudaMallocHost((void**)&ctx->h_state, sizeof(SegState) * nseg));
         ctx->h_state_cap = nseg;
     }
-    if ((rc = icp_reserve(ctx, &ctx->partial, &ctx->partial_cap, (size_t)nseg * ICP_NPARTS * bps * ICP_PART_STRIDE))) return rc;
+    if ((rc = icp_reserve(ctx, &ctx->partial, &ctx->partial_cap, (size_t)nseg * bps * ICP_PART_STRIDE))) return rc;
     if ((rc = icp_reserve(ctx, &ctx->gsum, &ctx->gsum_cap, (size_t)nseg * ICP_PART_STRIDE))) return rc;
     if ((rc = icp_reserve(ctx, &ctx->gparts, &ctx->gparts_cap, (size_t)nseg * ICP_NPARTS * ICP_PART_STRIDE))) return rc;
     if ((rc = icp_reserve(ctx, &ctx->corr_pos, &ctx->corr_cap, (size_t)nseg * S.shape.pitch))) return rc;
@@ -753,6 +872,12 @@ int icp_run_loop(icpsymm_ctx* ctx, int max_iters, float thr, const float* T_init
         if ((rc = icp_reserve(ctx, &ctx->trace_diff, &ctx->trace_diff_cap, need))) return rc;
         ctx->trace_stride = n_search;
     }
+
+    if (!ctx->ev_begin) {
+        ICP_CUDA_CHECK(cudaEventCreate(&ctx->ev_begin));
+        ICP_CUDA_CHECK(cudaEventCreate(&ctx->ev_end));
+    }
+    ICP_CUDA_CHECK(cudaEventRecord(ctx->ev_begin, st));   // loop_ms covers everything from here: state set-up, tile order, loop
 
     LoopParams lp;
     lp.max_iters = max_iters;
@@ -775,7 +900,17 @@ int icp_run_loop(icpsymm_ctx* ctx, int max_iters, float thr, const float* T_init
         ia.has_origin = 1;
         for (int i = 0; i < 3; i++) ia.origin[i] = origin[i];
     }
-    init_state_kernel<<<(nseg + 127) / 128, 128, 0, st>>>(ctx->d_state, nseg, ia, T.bb_lo, T.bb_hi);
+    if (!ctx->d_ctrl) {
+        ICP_CUDA_CHECK(cudaMalloc((void**)&ctx->d_ctrl, sizeof(LoopCtrl)));
+        ICP_CUDA_CHECK(cudaMemsetAsync(ctx->d_ctrl, 0, sizeof(LoopCtrl), st));
+    }
+    uint32_t k1_grid;
+    {
+        const uint32_t wps = icp_part_tile_lo(bps, part0 + nparts) - icp_part_tile_lo(bps, part0) + 1u;
+        const uint32_t resident = (uint32_t)ctx->sm_count * (uint32_t)kNNBlocksPerSM;
+        k1_grid = nseg * wps < resident ? nseg * wps : resident;
+    }
+    init_state_kernel<<<(nseg + 127) / 128, 128, 0, st>>>(ctx->d_state, nseg, ia, T.bb_lo, T.bb_hi, (LoopCtrl*)ctx->d_ctrl, k1_grid);
     // ICPSYMM_OPT_WARM_START = 2 keeps the correspondences of the previous call as seeds of the first search
     // (frame-to-frame tracking); a seed is only ever a candidate, so the result stays exact
     if (!(ctx->opt_warm_start == 2 && ctx->have_corr))
@@ -784,16 +919,41 @@ int icp_run_loop(icpsymm_ctx* ctx, int max_iters, float thr, const float* T_init
     NNParams np;
     np.src = S.view(); np.tgt = T.view();
     np.state = ctx->d_state; np.lp = ctx->d_lp; np.corr_pos = ctx->corr_pos; np.partial = ctx->partial;
-    np.part_blocks = bps; np.part0 = part0; np.nparts = nparts;
+    np.tiles_max = bps; np.part0 = part0; np.nparts = nparts;
+    np.work_per_seg = icp_part_tile_lo(bps, part0 + nparts) - icp_part_tile_lo(bps, part0) + 1u;   // +1: floor of a smaller pair
+    np.total_work = nseg * np.work_per_seg;
+    {
+        const uint32_t resident = (uint32_t)ctx->sm_count * (uint32_t)kNNBlocksPerSM;   // persistent blocks
+        np.grid = np.total_work < resident ? np.total_work : resident;
+    }
     SolveParams sp;
     sp.state = ctx->d_state; sp.lp = ctx->d_lp; sp.partial = ctx->partial; sp.gsum = ctx->gsum; sp.gparts = ctx->gparts;
-    sp.src_counts = S.counts; sp.part_blocks = bps; sp.part0 = part0; sp.nparts = nparts;
+    sp.src_counts = S.counts; sp.tiles_max = bps; sp.part0 = part0; sp.nparts = nparts; sp.k1_grid = np.grid;
     sp.trace_T = ctx->opt_trace ? ctx->trace_T : nullptr;
     sp.trace_diff = ctx->opt_trace ? ctx->trace_diff : nullptr;
     sp.trace_stride = ctx->trace_stride; sp.mode = single_search ? 3 : 0;
-    if (!ctx->d_ctrl) {
-        ICP_CUDA_CHECK(cudaMalloc((void**)&ctx->d_ctrl, sizeof(LoopCtrl)));
-        ICP_CUDA_CHECK(cudaMemsetAsync(ctx->d_ctrl, 0, sizeof(LoopCtrl), st));
+    np.ctrl = (LoopCtrl*)ctx->d_ctrl; np.order = nullptr;
+    // most-expensive-first order of the first search (single pairs that fill the machine more than twice)
+    if (nseg == 1 && !ctx->opt_identity && ctx->opt_tile_order && np.total_work >= 2u * np.grid && T.shape.n_levels >= 4) {
+        const uint32_t work = np.total_work;
+        int rec_level = 1;   // records of level l hold the boxes of level l-1: the coarsest level with at least 1024 boxes
+        for (uint32_t l = T.shape.n_levels - 1; l >= 1; l--)
+            if (T.shape.level_cnt[l] * ICP_FAN >= 1024u || l == 1) { rec_level = (int)l; break; }
+        size_t cap = ctx->order_cap;
+        if ((rc = icp_reserve(ctx, &ctx->order_buf, &cap, (size_t)4 * work))) return rc;
+        ctx->order_cap = cap;
+        uint32_t *ka = ctx->order_buf, *kb = ka + work, *va = kb + work, *vb = va + work;
+        size_t temp_bytes = 0;
+        ICP_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, ka, kb, va, vb, (int)work, 0, 16, st));
+        {
+            char* tmp = (char*)ctx->order_temp;
+            if ((rc = icp_reserve(ctx, &tmp, &ctx->order_temp_bytes, temp_bytes))) return rc;
+            ctx->order_temp = tmp;
+        }
+        tile_cost_kernel<<<(work * 32u + 255u) / 256u, 256, 0, st>>>(S.view(), T.view(), ctx->d_state, part0, nparts, work,
+                                                                      rec_level, ka, va);
+        ICP_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(ctx->order_temp, temp_bytes, ka, kb, va, vb, (int)work, 0, 16, st));
+        np.order = vb;
     }
     sp.ctrl = (LoopCtrl*)ctx->d_ctrl; sp.use_cond = 0; sp.cond = 0;
     // single searches (find_correspondences, eval_diff, normal_equations) are LOCAL to the rank's shard: only
@@ -808,10 +968,6 @@ int icp_run_loop(icpsymm_ctx* ctx, int max_iters, float thr, const float* T_init
     const bool timing = ctx->opt_kernel_timing != 0;
     const bool use_graph = ctx->opt_use_graph && !timing && !single_search && !use_comm && stream_capturable(st);
 
-    if (!ctx->ev_begin) {
-        ICP_CUDA_CHECK(cudaEventCreate(&ctx->ev_begin));
-        ICP_CUDA_CHECK(cudaEventCreate(&ctx->ev_end));
-    }
     if (timing && ctx->ev_pool_n < 4 * n_search) {
         for (int i = 0; i < ctx->ev_pool_n; i++) cudaEventDestroy(ctx->ev_pool[i]);
         free(ctx->ev_pool);
@@ -827,7 +983,7 @@ int icp_run_loop(icpsymm_ctx* ctx, int max_iters, float thr, const float* T_init
         key.generation = ctx->generation;
         key.shard_rank = ctx->shard_rank; key.shard_world = ctx->shard_world; key.trace = ctx->opt_trace;
         key.trace_stride = ctx->opt_trace ? ctx->trace_stride : 0;
-        key.mode = ctx->opt_use_graph + 16 * ctx->peer_world;
+        key.mode = ctx->opt_use_graph + 16 * ctx->peer_world + (np.order ? 1024 : 0);
         if (!ctx->graph_exec || !(ctx->graph_key == key)) {
             if (ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }
             cudaGraph_t g = nullptr;
@@ -859,11 +1015,9 @@ int icp_run_loop(icpsymm_ctx* ctx, int max_iters, float thr, const float* T_init
             cudaGraphDestroy(g);
             ctx->graph_key = key;
         }
-        ICP_CUDA_CHECK(cudaEventRecord(ctx->ev_begin, st));
         ICP_CUDA_CHECK(cudaGraphLaunch(ctx->graph_exec, st));
         ICP_CUDA_CHECK(cudaEventRecord(ctx->ev_end, st));
     } else {
-        ICP_CUDA_CHECK(cudaEventRecord(ctx->ev_begin, st));
         for (int k = 0; k < n_search; k++)
             launch_iteration(ctx, np, sp, nseg, use_comm, timing ? ctx->ev_pool + 4 * k : nullptr);
         ICP_CUDA_CHECK(cudaEventRecord(ctx->ev_end, st));
@@ -889,6 +1043,7 @@ int icp_run_loop(icpsymm_ctx* ctx, int max_iters, float thr, const float* T_init
     for (uint32_t s = 0; s < nseg; s++) max_searches = ctx->h_state[s].searches > max_searches ? ctx->h_state[s].searches : max_searches;
     float search_ms = 0.f, solve_ms = 0.f;
     int search_launches = 0, solve_launches = 0;
+    ctx->timed_searches = timing ? (max_searches < n_search ? max_searches : n_search) : 0;
     if (timing) {
         for (int k = 0; k < max_searches && k < n_search; k++) {
             float a = 0.f, b = 0.f;
@@ -1010,6 +1165,19 @@ int icp_solve_compose_device(icpsymm_ctx* ctx, const double* sums, const double*
     return out[19] != 0.0 ? ICPSYMM_WARN_DEGENERATE : ICPSYMM_OK;
 }
 
+int icp_search_times(icpsymm_ctx* ctx, float* search_ms, float* solve_ms, int n) {
+    if (!ctx->h_state || ctx->ev_pool_n == 0) return icp_fail_msg(ctx, ICPSYMM_ERR_NOT_READY, "no registration with ICPSYMM_OPT_KERNEL_TIMING has run");
+    int k = 0;
+    for (; k < n && 4 * k + 3 < ctx->ev_pool_n && k < ctx->timed_searches; k++) {
+        float a = 0.f, b = 0.f;
+        if (cudaEventElapsedTime(&a, ctx->ev_pool[4 * k], ctx->ev_pool[4 * k + 1]) != cudaSuccess ||
+            cudaEventElapsedTime(&b, ctx->ev_pool[4 * k + 2], ctx->ev_pool[4 * k + 3]) != cudaSuccess) { cudaGetLastError(); break; }
+        if (search_ms) search_ms[k] = a;
+        if (solve_ms) solve_ms[k] = b;
+    }
+    return k;
+}
+
 #ifdef ICP_EXPERIMENT   // developer build only (make exp): seed-quality experiments, never in the shipped library
 namespace {
 __global__ void seed_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint32_t n, int mode) {
@@ -1042,12 +1210,5 @@ extern "C" int icpsymm_debug_seed(icpsymm_ctx* ctx, int mode) {
 }
 extern "C" int icpsymm_debug_single_search(icpsymm_ctx* ctx, const float* T16, icpsymm_stats* stats) {
     return icp_run_single(ctx, T16, nullptr, stats);
-}
-extern "C" int icpsymm_debug_search_times(icpsymm_ctx* ctx, float* search_ms, float* solve_ms, int n) {
-    for (int k = 0; k < n && 4 * k + 3 < ctx->ev_pool_n; k++) {
-        cudaEventElapsedTime(search_ms + k, ctx->ev_pool[4 * k], ctx->ev_pool[4 * k + 1]);
-        cudaEventElapsedTime(solve_ms + k, ctx->ev_pool[4 * k + 2], ctx->ev_pool[4 * k + 3]);
-    }
-    return 0;
 }
 #endif

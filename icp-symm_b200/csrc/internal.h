@@ -92,6 +92,8 @@ struct icpsymm_ctx {
     double* trace_diff = nullptr; size_t trace_diff_cap = 0;   // doubles
     int trace_stride = 0;
     void* io_buf = nullptr;       size_t io_bytes = 0;   // device scratch for exports/imports
+    uint32_t* order_buf = nullptr; size_t order_cap = 0;  // tile order of the first search: keys/values, double-buffered
+    void* order_temp = nullptr;   size_t order_temp_bytes = 0;
     bool have_corr = false;
 
     // options
@@ -105,6 +107,7 @@ struct icpsymm_ctx {
     int opt_trace = 0;
     int opt_grid_blocks = 0;
     int opt_async_setup = 0;
+    int opt_tile_order = 1;
     double opt_peer_timeout_ms = 10000.0;
 
     // graph cache
@@ -114,7 +117,7 @@ struct icpsymm_ctx {
 
     // timing
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
-    cudaEvent_t* ev_pool = nullptr; int ev_pool_n = 0;
+    cudaEvent_t* ev_pool = nullptr; int ev_pool_n = 0; int timed_searches = 0;
 
     // multi-GPU
     int shard_rank = 0, shard_world = 1;
@@ -158,6 +161,7 @@ int icp_export_transformed(icpsymm_ctx* ctx, const float* T, float* xyz_out, siz
 int icp_solve_compose_device(icpsymm_ctx* ctx, const double* sums, const double* origin, double* Tinc, double* x,
                              double* ratio);
 int icp_read_sums(icpsymm_ctx* ctx, double* sums, double* origin_out);
+int icp_search_times(icpsymm_ctx* ctx, float* search_ms, float* solve_ms, int n);
 
 // kabsch.cu
 int icp_kabsch(icpsymm_ctx* ctx, const double* src, const double* dst, size_t n, double R[9], double T[3]);

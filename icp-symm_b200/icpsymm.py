@@ -19,7 +19,7 @@ OK, WARN_DEGENERATE = 0, 1
 ERR_INVALID, ERR_CUDA, ERR_NOT_READY, ERR_SIZE, ERR_NONFINITE, ERR_COMM = -1, -2, -3, -4, -5, -6
 OPT_REL_DIFF_TOL, OPT_IDENTITY_PAIRS, OPT_MAX_PAIR_DIST, OPT_USE_GRAPH = 1, 2, 3, 4
 OPT_KERNEL_TIMING, OPT_WARM_START, OPT_TRACE, OPT_GRID_BLOCKS, OPT_ASYNC_SETUP = 5, 6, 7, 8, 9
-OPT_MIN_NORMAL_DOT, OPT_PEER_TIMEOUT_MS = 10, 11
+OPT_MIN_NORMAL_DOT, OPT_PEER_TIMEOUT_MS, OPT_TILE_ORDER = 10, 11, 12
 
 
 class Stats(C.Structure):
@@ -79,6 +79,7 @@ def load():
         "icpsymm_get_transformed_source": (C.c_int, [vp, fp, fp, sz]),
         "icpsymm_get_trace": (C.c_int, [vp, sz, C.c_int, fp, dp]),
         "icpsymm_register_npoint": (C.c_int, [vp, dp, dp, sz, dp, dp]),
+        "icpsymm_get_search_times": (C.c_int, [vp, fp, fp, C.c_int]),
         "icpsymm_comm_unique_id": (C.c_int, [vp]),
         "icpsymm_comm_init": (C.c_int, [vp, vp, C.c_int, C.c_int]),
         "icpsymm_comm_destroy": (C.c_int, [vp]),
@@ -92,6 +93,11 @@ def load():
         fn.restype, fn.argtypes = res, args
     _lib = L
     return L
+
+
+def tile_rows(n_points):
+    """fp64 rows K1 leaves per pair and search: one per 256-query tile (csrc/common.cuh)"""
+    return (n_points + 255) // 256
 
 
 def exported_symbols():
@@ -207,6 +213,15 @@ class Context:
         self._check(self.L.icpsymm_set_target_dev(self.h, C.c_void_p(dev_ptr), n, stride))
         self.n_tgt, self.n_pairs = n, 1
 
+    def set_source_batch_ptr(self, host_ptr, n_pairs, n, stride):
+        """host pointer variant (pinned buffers of the bench): n_pairs clouds of n points each"""
+        self._check(self.L.icpsymm_set_source_batch(self.h, C.c_void_p(host_ptr), None, n_pairs, n, stride))
+        self.n_pairs, self.n_src = n_pairs, n
+
+    def set_target_batch_ptr(self, host_ptr, n_pairs, n, stride):
+        self._check(self.L.icpsymm_set_target_batch(self.h, C.c_void_p(host_ptr), None, n_pairs, n, stride))
+        self.n_pairs, self.n_tgt = n_pairs, n
+
     def _set_batch(self, fn, xyz, counts):
         xyz = _f32(xyz)
         assert xyz.ndim == 3 and xyz.shape[2] >= 3
@@ -301,6 +316,12 @@ class Context:
         d = C.c_double()
         self._check(self.L.icpsymm_get_trace(self.h, pair, k, _fp(T), C.byref(d)))
         return T.reshape(4, 4), d.value
+
+    def search_times(self, n=64):
+        """per-launch ms of the last registration timed with OPT_KERNEL_TIMING: (search[k], solve[k])"""
+        a, b = np.zeros(n, np.float32), np.zeros(n, np.float32)
+        k = self._check(self.L.icpsymm_get_search_times(self.h, _fp(a), _fp(b), n))
+        return a[:k].copy(), b[:k].copy()
 
     def register_npoint(self, src, dst):
         """registrateNPoint (regist.h:8-72): dst = R src + T"""

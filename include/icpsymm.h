@@ -74,6 +74,8 @@ enum {
     ICPSYMM_OPT_GRID_BLOCKS = 8,    /* accepted and ignored: the tile -> block map of the search kernel is canonical (a function
                                        of the pair's point count only), which is what makes results independent of the GPU count */
     ICPSYMM_OPT_MIN_NORMAL_DOT = 10, /* <= -1 = off; reject pairs whose normals disagree: n_p . n_q < value */
+    ICPSYMM_OPT_TILE_ORDER = 12,    /* 1 (default) = hand the 256-query tiles of the first search out most expensive first (a cost
+                                       estimate per tile); 0 = curve order.  Scheduling only: results are identical */
     ICPSYMM_OPT_PEER_TIMEOUT_MS = 11, /* NVLink peer exchange: how long a rank waits for its peers' sums (default 10000 ms)
                                         before the call fails with ICPSYMM_ERR_COMM */
     ICPSYMM_OPT_ASYNC_SETUP = 9     /* 1 = set_source / set_target / estimate_normals return without waiting: each cloud is
@@ -143,6 +145,11 @@ int icpsymm_solve_compose(icpsymm_ctx* ctx, const double sums[ICPSYMM_NSUMS], co
 int icpsymm_get_transformed_source(icpsymm_ctx* ctx, const float T[16], float* xyz_out, size_t stride_bytes);
 /* per-search trace (ICPSYMM_OPT_TRACE): k = 0..searches-1 of pair `pair` */
 int icpsymm_get_trace(icpsymm_ctx* ctx, size_t pair, int k, float T[16], double* diff);
+
+/* per-launch device times of the last registration run with ICPSYMM_OPT_KERNEL_TIMING: search k (the
+ * NN+accumulate kernel) and the reduce+solve kernel that followed it, in ms; either array may be NULL.
+ * Returns the number of entries written (<= n), or a negative error. */
+int icpsymm_get_search_times(icpsymm_ctx* ctx, float* search_ms, float* solve_ms, int n);
 
 /* ---- closed-form point-to-point fit (registrateNPoint, regist.h:8-72): dst = R src + T, fp64 ---- */
 int icpsymm_register_npoint(icpsymm_ctx* ctx, const double* src_xyz, const double* dst_xyz, size_t n,

@@ -34,3 +34,9 @@ def bunny():
 @pytest.fixture(scope="session")
 def gold():
     return dict(np.load(os.path.join(GOLD, "cat_golden.npz")))
+
+
+@pytest.fixture(scope="session")
+def solve_gold():
+    """independent fp64 numpy.linalg.lstsq solve of the canonical iteration on cat (tests/golden/make_golden.py)"""
+    return dict(np.load(os.path.join(GOLD, "cat_solve_golden.npz")))

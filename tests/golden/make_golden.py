@@ -18,7 +18,9 @@ What is pinned here, independently of oracle/ (none of this imports the oracle):
       registrateNPoint (regist.h:8-72) via cv2.SVDecomp exactly as the reference calls it,
       exact fp32 brute-force 1-NN (+ OpenCV-bundled FLANN KDTREE_SINGLE, leaf 15: the
       pcl::KdTreeFLANN configuration),
-      k=10 PCA normals via scipy cKDTree + numpy eigh (PCL NormalEstimation restatement).
+      k=10 PCA normals via scipy cKDTree + numpy eigh (PCL NormalEstimation restatement),
+      the canonical joint 6-unknown solve by numpy.linalg.lstsq on the stacked rows + the composition of the
+      comment at func.cpp:94 (cat_solve_golden.npz) -- pins oracle and device solve_compose to a third derivation.
 """
 import os
 
@@ -116,6 +118,32 @@ def estimate_literal(src, sn, tgt, tn):
     return T.astype(np.float32), M, n.astype(np.float32), c, a_, t_
 
 
+def canonical_solve(p, n_p, q, n_q):
+    """Independent fp64 restatement of the canonical iteration (what func.cpp:43-60,85-99 intend):
+    rows [ (p~+q~) x n | n ] and residuals (p~-q~).n about the pair centroids, ONE joint least-squares solve by
+    numpy.linalg.lstsq (not normal equations, not LDL^T), theta = atan|a|, and the composition in the order of the
+    comment at func.cpp:94:  T = Tr(qbar) R(theta, a^) Tr(t cos theta) R(theta, a^) Tr(-pbar)."""
+    p, q = p.astype(np.float64), q.astype(np.float64)
+    n = n_p.astype(np.float64) + n_q.astype(np.float64)
+    pbar, qbar = p.mean(axis=0), q.mean(axis=0)
+    pc, qc = p - pbar, q - qbar
+    A = np.c_[np.cross(pc + qc, n), n]
+    b = -np.einsum("ij,ij->i", pc - qc, n)
+    x = np.linalg.lstsq(A, b, rcond=None)[0]
+    a, t = x[:3], x[3:]
+    th = np.arctan(np.linalg.norm(a))
+    u = a / np.linalg.norm(a)
+    K = np.array([[0, -u[2], u[1]], [u[2], 0, -u[0]], [-u[1], u[0], 0]])
+    R = np.eye(3) + np.sin(th) * K + (1 - np.cos(th)) * (K @ K)
+
+    def tr(v):
+        M = np.eye(4); M[:3, 3] = v
+        return M
+
+    R4 = np.eye(4); R4[:3, :3] = R
+    return x, tr(qbar) @ R4 @ tr(t * np.cos(th)) @ R4 @ tr(-pbar)
+
+
 def main():
     cat = read_pcd_xyz(f"{REF}/cat.pcd")
     cat_out = read_pcd_xyz(f"{REF}/cat_out.pcd")
@@ -180,6 +208,17 @@ def main():
         T = (inc @ T).astype(np.float32)
         diffs.append(eval_diff_seq(src, cat_out))
     g["lit_diffs"], g["lit_T_final"] = np.array(diffs, np.float32), T
+
+    # canonical joint solve, independent of the oracle and of the device code (same derivation nowhere else):
+    # identity pairs (what myicp.cpp:128-131 does) and exact-NN pairs, PCA normals from above
+    sol = {}
+    n_src, n_tgt = g["normals_cat"][:, :3], g["normals_cat_out"][:, :3]
+    sol["x_identity"], sol["T_identity"] = canonical_solve(cat, n_src, cat_out, n_tgt)
+    nn = g["nn_idx"]
+    sol["x_nn"], sol["T_nn"] = canonical_solve(cat, n_src, cat_out[nn], n_tgt[nn])
+    np.savez_compressed(f"{OUT}/cat_solve_golden.npz", **sol)
+    for k, v in sol.items():
+        print(k, np.asarray(v).shape, np.asarray(v).round(6).tolist() if np.asarray(v).size <= 6 else "")
 
     np.savez_compressed(f"{OUT}/cat_golden.npz", **g)
     for k, v in g.items():

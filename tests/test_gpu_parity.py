@@ -189,6 +189,31 @@ def test_solve_compose_device_vs_oracle(ctx, cat, cat_out, gold):
     assert rc == icp.WARN_DEGENERATE and dego == 1 and np.isfinite(Td).all() and np.allclose(Td, To, atol=1e-12)
 
 
+def test_solve_compose_matches_independent_lstsq_golden(ctx, cat, cat_out, gold, solve_gold):
+    """device normal equations (fp32 products, fp64 sums) + device solve against the independent numpy lstsq golden
+    (tests/golden/make_golden.py: canonical_solve), identity pairs and exact-NN pairs, golden PCA normals"""
+    ctx.set_source(cat); ctx.set_target(cat_out)
+    ctx.set_normals(0, gold["normals_cat"]); ctx.set_normals(1, gold["normals_cat_out"])
+    ext = wl.extent(cat)
+    for name, ident in (("nn", 0), ("identity", 1)):
+        ctx.set_option(icp.OPT_IDENTITY_PAIRS, ident)
+        try:
+            for origin in ((0.0, 0.0, 0.0), (10.0, 20.0, 30.0)):
+                S = ctx.normal_equations(None, origin)
+                T, x, rc, _ = ctx.solve_compose(S, origin)
+                assert rc == 0 and S[36] == len(cat)
+                assert np.allclose(x, solve_gold["x_" + name], rtol=1e-5, atol=1e-6)
+                assert wl.rotation_angle(T, solve_gold["T_" + name]) <= 1e-6
+                assert np.abs(T[:3, 3] - solve_gold["T_" + name][:3, 3]).max() <= 1e-6 * ext
+        finally:
+            ctx.set_option(icp.OPT_IDENTITY_PAIRS, 0)
+    # the device solve alone, fed with exact fp64 sums
+    idx = gold["nn_idx"]
+    S = orc.symm_accumulate(cat, gold["normals_cat"], cat_out[idx], gold["normals_cat_out"][idx], (0, 0, 0))
+    T, x, rc, _ = ctx.solve_compose(S, (0, 0, 0))
+    assert np.allclose(x, solve_gold["x_nn"], rtol=0, atol=1e-7) and wl.rotation_angle(T, solve_gold["T_nn"]) <= 1e-8
+
+
 def _register_and_compare(ctx, src, tgt, max_iters, thr, rel_tol=0.0, T_true=None, check_trace=True, match_iters=False):
     ctx.set_source(src)
     ctx.set_target(tgt)
@@ -216,10 +241,17 @@ def _register_and_compare(ctx, src, tgt, max_iters, thr, rel_tol=0.0, T_true=Non
         oi, od = orc.KdTree(tgt).nn(p)
         assert np.array_equal(idx, oi) and np.array_equal(d2, od)
         if check_trace:
-            for k in range(st["searches"]):
-                Tk, dk = ctx.trace(k)
-                oi, od = orc.KdTree(tgt).nn(orc.transform_points(Tk, src))
-                assert dk == pytest.approx(np.sqrt(od.astype(np.float64)).sum(), rel=1e-6)
+            # EVERY search of the loop, not only the last: the transform the loop held at search k, the device
+            # search under it (indices and fp32 distances bit-exact against the oracle) and the diff the loop saw
+            tree = orc.KdTree(tgt)
+            traced = [ctx.trace(k) for k in range(st["searches"])]
+            for k, (Tk, dk) in enumerate(traced):
+                oi, od = tree.nn(orc.transform_points(Tk, src))
+                assert dk == pytest.approx(np.sqrt(od.astype(np.float64)).sum(), rel=1e-6), k
+                ik, d2k = ctx.find_correspondences(Tk)
+                assert np.array_equal(ik, oi) and np.array_equal(d2k, od), k
+                if k < len(r["trace_T"]):   # the oracle's own transform at search k
+                    assert wl.rotation_angle(Tk, r["trace_T"][k]) <= ROT_TOL, k
         if T_true is not None:
             assert wl.rotation_angle(T, T_true) < 1e-4
     finally:
@@ -303,9 +335,34 @@ def test_register_bunny_config2(ctx, bunny):
     assert rc == icp.WARN_DEGENERATE and st["degenerate"] == 1 and np.isfinite(T).all()
 
 
+@pytest.mark.parametrize("case", ["cat", "synth50k"])
+def test_end_to_end_oracle_with_its_own_normals(ctx, cat, cat_out, case):
+    """whole RegisterSymm on both sides, nothing shared: oracle normals -> oracle loop against device normals -> device
+    loop (every other registration test hands the device's normals to the oracle to isolate the loop)"""
+    if case == "cat":
+        src, tgt, thr, rel = cat, cat_out, 1.0, 0.0
+    else:
+        src, tgt, _ = wl.config_synth(50_000)
+        thr, rel = 1.0, 1e-5
+    ns, _ = orc.estimate_normals(src, 10)
+    nt, _ = orc.estimate_normals(tgt, 10)
+    ctx.set_source(src); ctx.set_target(tgt); ctx.estimate_normals(10)
+    ctx.set_option(icp.OPT_REL_DIFF_TOL, rel)
+    try:
+        T, st, _ = ctx.register_symm(50, thr)
+    finally:
+        ctx.set_option(icp.OPT_REL_DIFF_TOL, 0.0)
+    r = orc.register_symm(src, ns, tgt, nt, max_iters=st["iters"], diff_threshold=thr if case == "cat" else -1.0)
+    assert r["iters"] == st["iters"]
+    ext = wl.extent(tgt)
+    assert wl.rotation_angle(T, r["T"]) <= ROT_TOL
+    assert np.abs(T[:3, 3].astype(np.float64) - r["T"][:3, 3]).max() <= TRANS_TOL * ext
+    assert st["rmse"] == pytest.approx(r["rmse"], rel=1e-4, abs=1e-7 * ext)
+
+
 def test_register_synth_100k(ctx):
     src, tgt, Ttrue = wl.config_synth(100_000)
-    _register_and_compare(ctx, src, tgt, 50, 1.0, rel_tol=1e-5, T_true=Ttrue, check_trace=False, match_iters=True)
+    _register_and_compare(ctx, src, tgt, 50, 1.0, rel_tol=1e-5, T_true=Ttrue, check_trace=True, match_iters=True)
 
 
 def test_max_pair_distance_rejection(ctx, cat, cat_out):
@@ -464,6 +521,15 @@ def test_full_size_1m_config3(ctx):
         T, st, _ = ctx.register_symm(50, 1.0)
         assert 0 < st["iters"] <= 50 and st["converged"] == 2 and st["degenerate"] == 0
         assert wl.rotation_angle(T, Ttrue) < 2e-5 and np.abs(T[:3, 3] - Ttrue[:3, 3]).max() < 2e-5 * wl.extent(tgt)
+        # the north-star bars at the headline size, against the ORACLE run on the same inputs (trip count pinned: a
+        # relative-change stop can fall either side of a rounding error)
+        r = orc.register_symm(src, ctx.get_normals(0), tgt, ctx.get_normals(1), max_iters=st["iters"], diff_threshold=-1.0)
+        assert r["iters"] == st["iters"]
+        assert wl.rotation_angle(T, r["T"]) <= ROT_TOL
+        assert np.abs(T[:3, 3].astype(np.float64) - r["T"][:3, 3]).max() <= TRANS_TOL * wl.extent(tgt)
+        assert st["rmse"] == pytest.approx(r["rmse"], rel=RMSE_RTOL)
+        assert np.array_equal(ctx.get_correspondences()[0], r["idx"]) or \
+            (ctx.get_correspondences()[0] != r["idx"]).mean() < 1e-4     # pairs that sit on a tie between the two transforms
         # final correspondences: bit-exact against the oracle fed with the device transform
         idx, d2 = ctx.get_correspondences()
         oi, od = tree.nn(orc.transform_points(T, src))

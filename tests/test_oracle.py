@@ -165,6 +165,23 @@ def test_canonical_recovers_fixture_truth(cat, cat_out, gold):
     assert r0["iters"] == 0 and np.array_equal(r0["T"], np.eye(4, dtype=np.float32))
 
 
+def test_solve_compose_matches_independent_lstsq_golden(cat, cat_out, gold, solve_gold):
+    """the 37 raw sums + algebraic re-centring + LDL^T + composition of the oracle against a third derivation:
+    numpy.linalg.lstsq on the explicitly centred stacked rows [ (p~+q~) x n | n ] (func.cpp:43-60,85-88) and the
+    composition of the comment at func.cpp:94 -- for identity pairs and for exact-NN pairs, for two origins"""
+    ns, nt = gold["normals_cat"], gold["normals_cat_out"]
+    for name, idx in (("identity", np.arange(len(cat))), ("nn", gold["nn_idx"])):
+        for origin in ((0.0, 0.0, 0.0), (10.0, 20.0, 30.0)):
+            S = orc.symm_accumulate(cat, ns, cat_out[idx], nt[idx], origin)
+            T, x, deg = orc.solve_compose(S, origin)
+            assert deg == 0
+            assert np.allclose(x, solve_gold["x_" + name], rtol=0, atol=1e-7)
+            assert wl.rotation_angle(T, solve_gold["T_" + name]) <= 1e-8
+            assert np.abs(T[:3, 3] - solve_gold["T_" + name][:3, 3]).max() <= 1e-9 * wl.extent(cat)
+    # the identity-pair solve IS the fixture's known answer (main.cpp:44-52): one iteration suffices (SURVEY section 0)
+    assert wl.rotation_angle(solve_gold["T_identity"], gold["truth_R"]) < 1e-7
+
+
 def test_accumulate_matches_literal_rows_and_recentring(cat, cat_out, gold):
     """sum of Oracle-L rows (func.cpp:43-60) == Oracle-C raw sums about origin 0; re-centring is exact algebra."""
     ns, nt = gold["normals_cat"], gold["normals_cat_out"]

@@ -27,6 +27,8 @@ def child(lib, n):
         L = ctx.L
         stream = torch.cuda.ExternalStream(ctx.stream)
         ctx.set_option(icp.OPT_REL_DIFF_TOL, 1e-5)
+        if os.environ.get("TILE_ORDER"):
+            ctx.set_option(icp.OPT_TILE_ORDER, int(os.environ["TILE_ORDER"]))
         import time
         tn = []
         for _ in range(5):
@@ -44,21 +46,15 @@ def child(lib, n):
         h1 = hashlib.md5(idx.tobytes() + d2.tobytes()).hexdigest()[:8]
         h2 = hashlib.md5(np.ascontiguousarray(Tm).tobytes()).hexdigest()[:8]
         per = ""
-        if hasattr(L, "icpsymm_debug_search_times"):
-            ctx.set_option(icp.OPT_KERNEL_TIMING, 1)
-            best = None
-            for _ in range(4):
-                with torch.cuda.stream(stream):
-                    flush.zero_()
-                _, st2, _ = ctx.register_symm(50, 1.0)
-                k = st2["searches"]
-                a = (C.c_float * k)(); b = (C.c_float * k)()
-                L.icpsymm_debug_search_times.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int]
-                L.icpsymm_debug_search_times(ctx.h, a, b, k)
-                cur = np.array(list(a))
-                best = cur if best is None else np.minimum(best, cur)
-                solve = float(np.mean(list(b)))
-            per = " searches[" + " ".join(f"{x:.3f}" for x in best) + f"] solve {solve*1e3:.1f}us"
+        ctx.set_option(icp.OPT_KERNEL_TIMING, 1)
+        best = None
+        for _ in range(4):
+            with torch.cuda.stream(stream):
+                flush.zero_()
+            ctx.register_symm(50, 1.0)
+            cur, sol = ctx.search_times()
+            best = cur if best is None else np.minimum(best, cur)
+        per = " searches[" + " ".join(f"{x:.3f}" for x in best) + f"] solve {float(sol.mean())*1e3:.1f}us"
         ms = sorted(ms[2:])
         print(f"{os.path.basename(lib):28s} loop best {ms[0]:.3f} med {ms[len(ms)//2]:.3f} iters {st['iters']}{per} normals(both) {min(tn)*1e3:.3f} corr {h1} T {h2} nrm {h3}",
               flush=True)
