@@ -110,7 +110,11 @@ struct SegState {
     int done;            // 0 = running
     int converged;       // 1 diff<=thr, 2 rel tol, 0 max iters
     int degenerate;
+    int track;           // walks of the next search record margins (the last step was small, see solve_kernel)
+    int have_margins;    // the search that ran last recorded margins
     int pad;
+    double radius;       // half diagonal of the target's bounding box
+    double spacing;      // typical point spacing of the target taken as a surface: extent / sqrt(points)
 };
 
 struct LoopParams {
@@ -122,6 +126,7 @@ struct LoopParams {
     int identity_pairs;
     int warm_start;
     int trace;
+    int skip_walk;       // 1 = skip the walk of a unit whose winners provably stand (margin test in K1)
 };
 
 // ---- pinned fp32 arithmetic -------------------------------------------------------------

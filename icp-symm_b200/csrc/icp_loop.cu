@@ -71,6 +71,9 @@ constexpr int kNNBlocksPerSM = 1024 / kNNThreads;   // 64 registers per thread: 
 #define ICP_TILES_PER_TICKET 1
 #endif
 constexpr int kTilesPerTicket = ICP_TILES_PER_TICKET;
+#ifndef ICP_TRACK_STEP_SPACINGS
+#define ICP_TRACK_STEP_SPACINGS 4.0   // record margins once a step moves no point by more than this many point spacings
+#endif
 constexpr int kNNWarps = kNNThreads / 32;
 #ifndef ICP_K2_THREADS
 #define ICP_K2_THREADS 1024
@@ -89,6 +92,12 @@ struct NNParams {
     double* partial;          // [pair][tiles_max] rows of ICP_PART_STRIDE doubles: one row per 256-query tile
     LoopCtrl* ctrl;           // ticket counter of the dynamic tile hand-out
     const uint32_t* order;    // ticket -> work item (null: identity)
+    // walk skipping (see the skip test in K1): per query the margin of its last tracked walk and the search in which
+    // that walk happened, per pair the fp32 transform of every search so far
+    float* margin2;
+    uint8_t* ref_search;      // 0xff = the query has no margin (never walked with tracking in this registration)
+    const float* hist;
+    uint32_t hist_stride;     // searches kept per pair
     uint32_t tiles_max;       // rows reserved per pair = icp_tiles(largest pair)
     uint32_t part0, nparts;   // parts of every pair this launch covers: 0, 8 = whole pairs; a query shard = a run of parts
     uint32_t work_per_seg;    // tile slots per pair handed out by this launch (the parts' tile range of the largest pair)
@@ -106,6 +115,8 @@ struct SolveParams {
     const uint32_t* src_counts;
     double* gsum;             // [pair][ICP_PART_STRIDE]: totals of the local parts (single searches)
     double* gparts;           // [pair][ICP_NPARTS][ICP_PART_STRIDE]: part sums, exchange buffer of the NCCL mode
+    float* hist;              // [pair][hist_stride][12]: the fp32 transform of every search (K1's skip test)
+    uint32_t hist_stride;
     float* trace_T;
     double* trace_diff;
     uint32_t tiles_max, part0, nparts, k1_grid;
@@ -125,7 +136,8 @@ struct InitArgs {
 __global__ void set_lp_kernel(LoopParams* dst, LoopParams v) { *dst = v; }
 
 __global__ void init_state_kernel(SegState* state, uint32_t nseg, InitArgs a, const float4* __restrict__ bb_lo,
-                                  const float4* __restrict__ bb_hi, LoopCtrl* ctrl, uint32_t k1_grid) {
+                                  const float4* __restrict__ bb_hi, const uint32_t* __restrict__ tgt_counts, LoopCtrl* ctrl,
+                                  uint32_t k1_grid, float* hist, uint32_t hist_stride) {
     uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s == 0) ctrl->work = k1_grid;   // tickets below the grid size are implicit
     if (s >= nseg) return;
@@ -135,6 +147,7 @@ __global__ void init_state_kernel(SegState* state, uint32_t nseg, InitArgs a, co
         float v = a.has_T ? a.T[i] : ((i % 5 == 0) ? 1.f : 0.f);
         st.T[i] = (double)v;
         st.Tf[i] = v;
+        if (hist) hist[(size_t)s * hist_stride * 12 + i] = v;   // the transform of search 0
     }
     float4 lo = bb_lo[s], hi = bb_hi[s];
     // the origin of the raw sums must be exactly representable in fp32 (K1 subtracts it in fp32)
@@ -142,6 +155,9 @@ __global__ void init_state_kernel(SegState* state, uint32_t nseg, InitArgs a, co
     st.origin[1] = a.has_origin ? (double)(float)a.origin[1] : (double)(0.5f * (lo.y + hi.y));
     st.origin[2] = a.has_origin ? (double)(float)a.origin[2] : (double)(0.5f * (lo.z + hi.z));
     st.min_ratio = 1.0;
+    const double ex = (double)hi.x - lo.x, ey = (double)hi.y - lo.y, ez = (double)hi.z - lo.z;
+    st.radius = 0.5 * sqrt(ex * ex + ey * ey + ez * ez);
+    st.spacing = 2.0 * st.radius / sqrt((double)(tgt_counts[s] ? tgt_counts[s] : 1u));
     state[s] = st;
 }
 
@@ -219,6 +235,8 @@ __global__ void __launch_bounds__(kNNThreads, kNNBlocksPerSM) nn_accum_kernel(co
     // memory comes out of the SM's L1 (4 blocks x this), and the walk lives on its L1 hit rate
     __shared__ float wacc[2][kTilesPerTicket][kNNWarps][ICP_PART_STRIDE];
     __shared__ int sDone;
+    __shared__ uint32_t sSearch;      // index of the running search of the block's current pair
+    __shared__ int sTrack;            // walks of this search record margins (K2 expects the next step to be small)
     __shared__ uint32_t sWork[2];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const LoopParams lp = *P.lp;
@@ -240,7 +258,7 @@ __global__ void __launch_bounds__(kNNThreads, kNNBlocksPerSM) nn_accum_kernel(co
         const uint32_t seg = we / tickets_per_seg;
         if (seg != cur_seg) {   // block-uniform: (re)load the pair's transform and origin
             const SegState* st = P.state + seg;
-            if (tid == 0) sDone = st->done;
+            if (tid == 0) { sDone = st->done; sSearch = (uint32_t)st->searches; sTrack = st->track; }
             if (tid < 12) sT[tid] = st->Tf[tid];
             if (tid < 3) sO[tid] = (float)st->origin[tid];
             __syncthreads();
@@ -273,6 +291,16 @@ __global__ void __launch_bounds__(kNNThreads, kNNBlocksPerSM) nn_accum_kernel(co
         float3 p = make_float3(0.f, 0.f, 0.f);
         Best b;
         best_init(b);
+        // SKIP TEST.  The last tracked walk of a query (search `ref`, query position x_ref = T_ref p) left its winner and
+        // its margin m: every other target point is at least m away from x_ref.  The query now sits at x = T p,
+        // delta = |x - x_ref| away, so every other point is at least m - delta from x (triangle inequality), while
+        // the old winner is d1 = |x - q| away.  If d1 < m - delta the winner cannot have changed: the lane keeps it
+        // and sits out the walk; a unit whose 32 lanes all keep theirs does not walk at all.  The three lengths are
+        // evaluated in fp32 with the rounding directed against keeping and a relative slack of 1e-5, three orders
+        // above the rounding of the pinned distance formula, so the statement also holds for the fp32 values the
+        // oracle compares (a tie has zero margin and never keeps).
+        const bool may_skip = lp.skip_walk && lp.warm_start && !lp.identity_pairs;
+        bool keep = false;   // this lane's winner provably stands
         if (active) {
             const float4 s = ldg4(spts + i);
             p = apply_rn(sT, s.x, s.y, s.z);
@@ -282,12 +310,32 @@ __global__ void __launch_bounds__(kNNThreads, kNNBlocksPerSM) nn_accum_kernel(co
             } else {
                 uint32_t prev = lp.warm_start ? corr[i] : 0xffffffffu;
                 if (prev < nt) best_offer(b, ldg4(tpts + prev), p.x, p.y, p.z);
+                const uint32_t ref = may_skip ? (uint32_t)P.ref_search[(size_t)seg * P.src.shape.pitch + i] : 0xffu;
+                if (ref < P.hist_stride && ref != 0xffu && prev < nt) {
+                    const float3 xr = apply_rn(P.hist + ((size_t)seg * P.hist_stride + ref) * 12, s.x, s.y, s.z);
+                    const float delta = __fsqrt_ru(dist2_rn(p.x, p.y, p.z, xr.x, xr.y, xr.z));
+                    const float d1 = __fsqrt_ru(b.d2());
+                    const float m = __fsqrt_rd(P.margin2[(size_t)seg * P.src.shape.pitch + i]);
+                    keep = __fmul_ru(__fadd_ru(d1, delta), 1.00001f) < __fmul_rd(m, 0.99999f);
+                }
             }
         }
-        // warp-synchronous exact search: the 32 lanes are 32 neighbouring source points
-        // (split units, see finish_units_kernel in index_build.cu, are not walked per cluster here: wrapping this walk in a
-        // pass loop costs the common case 15 %, far more than the rare split unit costs)
-        if (!lp.identity_pairs && nt > 0) nn_traverse_warp(P.tgt.shape, tbox, tpts, p.x, p.y, p.z, active, 0u, b);
+        // warp-synchronous exact search: the 32 lanes are 32 neighbouring source points; lanes that keep their winner
+        // are bystanders (split units, see finish_units_kernel in index_build.cu, are not walked per cluster here:
+        // wrapping this walk in a pass loop costs the common case 15 %, far more than the rare split unit costs)
+        const bool walk = active && !keep;
+        if (!lp.identity_pairs && nt > 0 && __any_sync(0xffffffffu, walk)) {
+            uint8_t* ref_slot = P.ref_search + (size_t)seg * P.src.shape.pitch + i;
+            if (sTrack && may_skip && sSearch < 0xffu) {
+                const WalkResult r = nn_walk<true>(&P.tgt.shape, tbox, tpts, p.x, p.y, p.z, walk, b.key);
+                b.key = r.key;
+                if (walk) { P.margin2[(size_t)seg * P.src.shape.pitch + i] = __uint_as_float(r.m2); *ref_slot = (uint8_t)sSearch; }
+            } else {
+                const WalkResult r = nn_walk<false>(&P.tgt.shape, tbox, tpts, p.x, p.y, p.z, walk, b.key);
+                b.key = r.key;
+                if (walk && may_skip) *ref_slot = 0xffu;   // walked without tracking: the old margin belongs to another winner
+            }
+        }
         float v[40];   // declared after the walk so that none of it is live across it; ICP_NSUMS = 37 used
 #pragma unroll
         for (int k = 0; k < 40; k++) v[k] = 0.f;
@@ -728,6 +776,25 @@ __global__ void __launch_bounds__(kSolveThreads) solve_kernel(const __grid_const
     mat34_mul(Tinc, Told, Tn);                                                                 // myicp.cpp:138
 #pragma unroll
     for (int i = 0; i < 12; i++) { st->T[i] = Tn[i]; st->Tf[i] = (float)Tn[i]; }
+    if (P.hist && (uint32_t)(k + 1) < P.hist_stride) {   // the transform search k+1 will use
+        float* h = P.hist + ((size_t)seg * P.hist_stride + (uint32_t)(k + 1)) * 12;
+#pragma unroll
+        for (int i = 0; i < 12; i++) h[i] = (float)Tn[i];
+    }
+    {
+        // how far can this step move a source point?  |step at the box centre| + rotation angle x box radius.  When it
+        // is within a few point spacings the NEXT step will be far smaller (the loop converges geometrically), so the
+        // margins the next search records will let most of the searches after it skip their walks (K1 skip test);
+        // before that, recording margins is wasted work (+15-20 % per walk), so the early searches do without.
+        const double cx = origin[0], cy = origin[1], cz = origin[2];
+        const double mx = Tinc[0] * cx + Tinc[1] * cy + Tinc[2] * cz + Tinc[3] - cx;
+        const double my = Tinc[4] * cx + Tinc[5] * cy + Tinc[6] * cz + Tinc[7] - cy;
+        const double mz = Tinc[8] * cx + Tinc[9] * cy + Tinc[10] * cz + Tinc[11] - cz;
+        const double an = sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
+        const double step = sqrt(mx * mx + my * my + mz * mz) + 2.0 * atan(an) * st->radius;
+        st->have_margins = st->track;   // what the search that has just run recorded
+        st->track = step < ICP_TRACK_STEP_SPACINGS * st->spacing ? 1 : 0;
+    }
     st->iter = st->iter + 1;
     st->pairs = (unsigned long long)(sS[36] + 0.5);
     ICP_K2_STAMP(3);
@@ -864,6 +931,10 @@ int icp_run_loop(icpsymm_ctx* ctx, int max_iters, float thr, const float* T_init
     if ((rc = icp_reserve(ctx, &ctx->gsum, &ctx->gsum_cap, (size_t)nseg * ICP_PART_STRIDE))) return rc;
     if ((rc = icp_reserve(ctx, &ctx->gparts, &ctx->gparts_cap, (size_t)nseg * ICP_NPARTS * ICP_PART_STRIDE))) return rc;
     if ((rc = icp_reserve(ctx, &ctx->corr_pos, &ctx->corr_cap, (size_t)nseg * S.shape.pitch))) return rc;
+    const uint32_t hist_stride = (uint32_t)(single_search ? 1 : max_iters + 2);
+    if ((rc = icp_reserve(ctx, &ctx->margin2, &ctx->margin_cap, (size_t)nseg * S.shape.pitch))) return rc;
+    if ((rc = icp_reserve(ctx, &ctx->ref_search, &ctx->ref_cap, (size_t)nseg * S.shape.pitch))) return rc;
+    if ((rc = icp_reserve(ctx, &ctx->hist, &ctx->hist_cap, (size_t)nseg * hist_stride * 12))) return rc;
     if (!ctx->d_lp) ICP_CUDA_CHECK(cudaMalloc((void**)&ctx->d_lp, sizeof(LoopParams)));
     const int n_search = single_search ? 1 : max_iters + 1;
     if (ctx->opt_trace) {
@@ -888,6 +959,7 @@ int icp_run_loop(icpsymm_ctx* ctx, int max_iters, float thr, const float* T_init
     lp.identity_pairs = ctx->opt_identity;
     lp.warm_start = ctx->opt_warm_start;
     lp.trace = ctx->opt_trace;
+    lp.skip_walk = ctx->opt_skip_walk;
     set_lp_kernel<<<1, 1, 0, st>>>(ctx->d_lp, lp);
 
     InitArgs ia;
@@ -910,7 +982,10 @@ int icp_run_loop(icpsymm_ctx* ctx, int max_iters, float thr, const float* T_init
         const uint32_t resident = (uint32_t)ctx->sm_count * (uint32_t)kNNBlocksPerSM;
         k1_grid = nseg * wps < resident ? nseg * wps : resident;
     }
-    init_state_kernel<<<(nseg + 127) / 128, 128, 0, st>>>(ctx->d_state, nseg, ia, T.bb_lo, T.bb_hi, (LoopCtrl*)ctx->d_ctrl, k1_grid);
+    init_state_kernel<<<(nseg + 127) / 128, 128, 0, st>>>(ctx->d_state, nseg, ia, T.bb_lo, T.bb_hi, T.counts, (LoopCtrl*)ctx->d_ctrl, k1_grid, ctx->hist,
+                                                           hist_stride);
+    // no unit has walked yet in this registration: nothing can be skipped in the first search
+    ICP_CUDA_CHECK(cudaMemsetAsync(ctx->ref_search, 0xff, (size_t)nseg * S.shape.pitch, st));
     // ICPSYMM_OPT_WARM_START = 2 keeps the correspondences of the previous call as seeds of the first search
     // (frame-to-frame tracking); a seed is only ever a candidate, so the result stays exact
     if (!(ctx->opt_warm_start == 2 && ctx->have_corr))
@@ -928,11 +1003,13 @@ int icp_run_loop(icpsymm_ctx* ctx, int max_iters, float thr, const float* T_init
     }
     SolveParams sp;
     sp.state = ctx->d_state; sp.lp = ctx->d_lp; sp.partial = ctx->partial; sp.gsum = ctx->gsum; sp.gparts = ctx->gparts;
+    sp.hist = ctx->hist; sp.hist_stride = hist_stride;
     sp.src_counts = S.counts; sp.tiles_max = bps; sp.part0 = part0; sp.nparts = nparts; sp.k1_grid = np.grid;
     sp.trace_T = ctx->opt_trace ? ctx->trace_T : nullptr;
     sp.trace_diff = ctx->opt_trace ? ctx->trace_diff : nullptr;
     sp.trace_stride = ctx->trace_stride; sp.mode = single_search ? 3 : 0;
     np.ctrl = (LoopCtrl*)ctx->d_ctrl; np.order = nullptr;
+    np.margin2 = ctx->margin2; np.ref_search = ctx->ref_search; np.hist = ctx->hist; np.hist_stride = hist_stride;
     // most-expensive-first order of the first search (single pairs that fill the machine more than twice)
     if (nseg == 1 && !ctx->opt_identity && ctx->opt_tile_order && np.total_work >= 2u * np.grid && T.shape.n_levels >= 4) {
         const uint32_t work = np.total_work;

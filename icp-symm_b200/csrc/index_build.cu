@@ -708,6 +708,7 @@ template int icp_reserve<unsigned long long>(icpsymm_ctx*, unsigned long long**,
 template int icp_reserve<double>(icpsymm_ctx*, double**, size_t*, size_t);
 template int icp_reserve<float>(icpsymm_ctx*, float**, size_t*, size_t);
 template int icp_reserve<char>(icpsymm_ctx*, char**, size_t*, size_t);
+template int icp_reserve<uint8_t>(icpsymm_ctx*, uint8_t**, size_t*, size_t);
 template int icp_reserve<SegState>(icpsymm_ctx*, SegState**, size_t*, size_t);
 
 cudaStream_t icp_cloud_stream(icpsymm_ctx* ctx, CloudSet& cs) {

@@ -66,8 +66,13 @@ __device__ __forceinline__ void scan_leaf(const float4* __restrict__ seg_pts, ui
 // when its d2 does not exceed the lane's bound (equal d2: the lower original index wins), so when no
 // taking lane has min d2 <= bound the scan changes nothing.  Returns whether some taking lane's bound
 // changed (warp-uniform).  `take` = false: the lane is a bystander and keeps its state.
+//
+// m2 (the "margin", see NNVisitor) collects the smallest squared distance of any point OTHER than the lane's
+// best: in the common case every point of the group is farther than the bound, hence not the best, and the
+// group's minimum is all that is needed; otherwise the loser of every key comparison is recorded.
+template <bool TRACK>
 __device__ __forceinline__ bool scan_leaf_lazy(const float4* __restrict__ seg_pts, uint32_t g, const NegQuery& nq,
-                                               bool take, Best& b) {
+                                               bool take, Best& b, uint32_t& m2) {
     const float4* lp = seg_pts + (size_t)g * ICP_LEAF;
     float4 c[ICP_LEAF];
     float d[ICP_LEAF];
@@ -77,12 +82,25 @@ __device__ __forceinline__ bool scan_leaf_lazy(const float4* __restrict__ seg_pt
     for (int j = 0; j < ICP_LEAF; j++) d[j] = dist2_packed(nq, c[j]);
     const float m = fminf(fminf(fminf(d[0], d[1]), fminf(d[2], d[3])), fminf(fminf(d[4], d[5]), fminf(d[6], d[7])));
     const uint32_t bound = (uint32_t)(b.key >> 32);
-    if (!__any_sync(0xffffffffu, take && __float_as_uint(m) <= bound)) return false;
+    if (!__any_sync(0xffffffffu, take && __float_as_uint(m) <= bound)) {
+        if (TRACK) m2 = min(m2, __float_as_uint(m));   // all eight are beyond the bound: none of them is the best
+        return false;
+    }
     if (take) {
+        const unsigned long long old = b.key;
 #pragma unroll
         for (int j = 0; j < ICP_LEAF; j++) {
             const unsigned long long k = ((unsigned long long)__float_as_uint(d[j]) << 32) | __float_as_uint(c[j].w);
             b.key = k < b.key ? k : b.key;
+        }
+        // every point that is not the (new) best is an "other" point: the eight of this group, and the previous best
+        // if it lost its place (the same point met twice -- a seed and its leaf -- has the best's own index)
+        if (TRACK) {
+            const uint32_t best_id = (uint32_t)b.key;
+            if ((uint32_t)old != best_id && (uint32_t)old != (uint32_t)ICP_INVALID_ID) m2 = min(m2, (uint32_t)(old >> 32));
+#pragma unroll
+            for (int j = 0; j < ICP_LEAF; j++)
+                m2 = min(m2, __float_as_uint(c[j].w) != best_id ? __float_as_uint(d[j]) : 0xffffffffu);
         }
     }
     return __any_sync(0xffffffffu, take && (uint32_t)(b.key >> 32) != bound);
@@ -126,7 +144,7 @@ __device__ __forceinline__ uint32_t point_box_bits(float lx, float ly, float lz,
 // warp-uniform 16-byte loads, packed arithmetic, no shuffles and no loop.  Returns the lane's
 // pass mask; kmin receives the lane's nearest passing child as (bound & ~7) | child.
 __device__ __forceinline__ uint32_t dense_children_test(const WideNode* __restrict__ nd, float qx, float qy, float qz,
-                                                        uint32_t my_bound, uint32_t& kmin) {
+                                                        uint32_t my_bound, uint32_t& kmin, uint32_t (&bb)[ICP_FAN]) {
     const float4* p4 = reinterpret_cast<const float4*>(nd);
     float4 r[12];
 #pragma unroll
@@ -144,6 +162,7 @@ __device__ __forceinline__ uint32_t dense_children_test(const WideNode* __restri
 #pragma unroll
         for (int c = 0; c < 4; c++) {
             const bool pass = b[c] <= my_bound && b[c] != ICP_INF_BITS;
+            bb[4 * h + c] = b[c];
             mine |= pass ? (1u << (4 * h + c)) : 0u;
             kmin = min(kmin, pass ? ((b[c] & ~7u) | (uint32_t)(4 * h + c)) : 0xffffffffu);
         }
@@ -153,14 +172,22 @@ __device__ __forceinline__ uint32_t dense_children_test(const WideNode* __restri
 
 // far_mode: the bounds are much larger than the patch (first iterations of a badly aligned pair), so
 // the patch box would prune next to nothing: go straight to the exact test of all 8 children.
+// Every child the WARP does not enter is reported to the visitor with the lane's own lower bound of it
+// (v.prune): that is how a lane learns how far away everything it did not look at must be.
+template <typename V>
 __device__ __forceinline__ uint32_t warp_node_test(const WideNode* __restrict__ nd, float qx, float qy, float qz,
                                                    uint32_t my_bound, bool active, const WarpPatch& pb,
-                                                   uint32_t max_bound, bool far_mode, int& pref) {
+                                                   uint32_t max_bound, bool far_mode, int& pref, V& v) {
     if (far_mode) {
-        uint32_t kmin;
-        const uint32_t mine = dense_children_test(nd, qx, qy, qz, my_bound, kmin);
+        uint32_t kmin, bb[ICP_FAN];
+        const uint32_t mine = dense_children_test(nd, qx, qy, qz, my_bound, kmin, bb);
         pref = (int)(__reduce_min_sync(0xffffffffu, active ? kmin : 0xffffffffu) & 7u);
-        return __reduce_or_sync(0xffffffffu, active ? mine : 0u);
+        const uint32_t mask = __reduce_or_sync(0xffffffffu, active ? mine : 0u);
+        if (V::kTrackMargin) {
+#pragma unroll
+            for (int c = 0; c < ICP_FAN; c++) v.prune(((mask >> c) & 1u) ? 0xffffffffu : bb[c]);
+        }
+        return mask;
     }
     const int cl = threadIdx.x & 7;
     const float* f = reinterpret_cast<const float*>(nd);
@@ -179,10 +206,16 @@ __device__ __forceinline__ uint32_t warp_node_test(const WideNode* __restrict__ 
     // stage 2: exact, per lane, only for the survivors
     uint32_t mask2 = 0;
     if (__popc(mask1) >= ICP_DENSE_MIN) {
-        uint32_t kmin;
-        const uint32_t mine = dense_children_test(nd, qx, qy, qz, my_bound, kmin);
+        uint32_t kmin, bb[ICP_FAN];
+        const uint32_t mine = dense_children_test(nd, qx, qy, qz, my_bound, kmin, bb);
         mask2 = __reduce_or_sync(0xffffffffu, active ? mine : 0u) & mask1;
+        if (V::kTrackMargin) {
+#pragma unroll
+            for (int c = 0; c < ICP_FAN; c++) v.prune(((mask2 >> c) & 1u) ? 0xffffffffu : bb[c]);
+        }
     } else {
+        // children cut by the patch test: the patch bound is a lower bound for every lane of the patch
+        if (V::kTrackMargin) v.prune(__reduce_min_sync(0xffffffffu, pass1 ? 0xffffffffu : lbp));
         for (uint32_t mm = mask1; mm; mm &= mm - 1) {
             const int c = __ffs((int)mm) - 1;
             const float lx = __shfl_sync(0xffffffffu, blx, c), ly = __shfl_sync(0xffffffffu, bly, c);
@@ -190,18 +223,22 @@ __device__ __forceinline__ uint32_t warp_node_test(const WideNode* __restrict__ 
             const float hy = __shfl_sync(0xffffffffu, bhy, c), hz = __shfl_sync(0xffffffffu, bhz, c);
             const uint32_t lb = point_box_bits(lx, ly, lz, hx, hy, hz, qx, qy, qz);
             if (__any_sync(0xffffffffu, active && lb <= my_bound && lb != ICP_INF_BITS)) mask2 |= 1u << c;
+            else if (V::kTrackMargin) v.prune(lb);
         }
     }
     return mask2;
 }
 
 // exact re-test of one child (slot c of record nd) under the current bounds
+template <typename V>
 __device__ __forceinline__ bool warp_child_recheck(const WideNode* __restrict__ nd, int c, float qx, float qy, float qz,
-                                                   uint32_t my_bound, bool active) {
+                                                   uint32_t my_bound, bool active, V& v) {
     const float* f = reinterpret_cast<const float*>(nd) + c;
     const uint32_t lb = point_box_bits(__ldg(f), __ldg(f + 8), __ldg(f + 16), __ldg(f + 24), __ldg(f + 32),
                                        __ldg(f + 40), qx, qy, qz);
-    return __any_sync(0xffffffffu, active && lb <= my_bound && lb != ICP_INF_BITS);
+    const bool enter = __any_sync(0xffffffffu, active && lb <= my_bound && lb != ICP_INF_BITS);
+    if (V::kTrackMargin && !enter) v.prune(lb);
+    return enter;
 }
 
 // The pending mask and the record pointer of the CURRENT node live in registers: a pop touches only
@@ -225,7 +262,7 @@ __device__ __forceinline__ void wide_traverse_group(const TreeShape& sh, const W
     uint32_t stale = 0;   // bit l: the pending mask of level l predates the latest bound improvement
     int l = top, pref;
     uint32_t i = 0;
-    uint32_t cur = warp_node_test(rec, qx, qy, qz, v.bound_bits(), active, pb, max_bound, far_mode, pref);
+    uint32_t cur = warp_node_test(rec, qx, qy, qz, v.bound_bits(), active, pb, max_bound, far_mode, pref, v);
     unsigned long long saved = 0ull;   // byte l-1: pending mask of the open ancestor at level l
     for (;;) {
         if (cur == 0u) {
@@ -240,7 +277,7 @@ __device__ __forceinline__ void wide_traverse_group(const TreeShape& sh, const W
         const int c = (pref >= 0 && ((cur >> pref) & 1u)) ? pref : (__ffs((int)cur) - 1);
         pref = -1;
         cur &= ~(1u << c);
-        if (((stale >> l) & 1u) && !warp_child_recheck(rec, c, qx, qy, qz, v.bound_bits(), active)) continue;
+        if (((stale >> l) & 1u) && !warp_child_recheck(rec, c, qx, qy, qz, v.bound_bits(), active, v)) continue;
         const uint32_t child = (i << ICP_LOG_FAN) + (uint32_t)c;
         ICP_ASSERT(l >= 1 && l <= top && i < sh.level_cnt[l] && child < sh.level_cnt[l - 1]);
         bool improved = false;
@@ -252,7 +289,7 @@ __device__ __forceinline__ void wide_traverse_group(const TreeShape& sh, const W
             saved = (saved & ~(0xffull << sh8)) | ((unsigned long long)cur << sh8);
             --l; i = child;
             rec = seg_nodes + sh.level_off[l] + i;
-            cur = warp_node_test(rec, qx, qy, qz, v.bound_bits(), active, pb, max_bound, far_mode, pref);
+            cur = warp_node_test(rec, qx, qy, qz, v.bound_bits(), active, pb, max_bound, far_mode, pref, v);
             stale &= ~(1u << l);
         }
         if (improved) {   // some active lane's bound improved (warp-uniform)
@@ -279,32 +316,55 @@ __device__ __forceinline__ void wide_traverse_warp(const TreeShape& sh, const Wi
     }
 }
 
+// m2, the MARGIN of the search: a lower bound (fp32 bits) of the squared distance from the query to every target
+// point other than the winner -- the smallest of (a) the distances of all points scanned that did not win and
+// (b) the lane's own lower bounds of all boxes the warp never entered.  Both are exact statements about the
+// pinned fp32 arithmetic (a box bound never exceeds the fp32 distance of a member point).  K1 stores it and uses it
+// in later searches: while the query has moved by less than the gap between the winner's distance and the margin,
+// the winner cannot have changed and the walk is skipped (icp_loop.cu).
+template <bool TRACK>
 struct NNVisitor {
+    static constexpr bool kTrackMargin = TRACK;
     Best& b;
     const float4* __restrict__ pts;
     float qx, qy, qz;
     NegQuery nq;
+    uint32_t m2;
     __device__ __forceinline__ uint32_t bound_bits() const { return (uint32_t)(b.key >> 32); }
     __device__ __forceinline__ void set_active(bool) {}
+    __device__ __forceinline__ void prune(uint32_t lower_bound_bits) { if (TRACK) m2 = min(m2, lower_bound_bits); }
     // warp-uniform call; returns whether some active lane's bound changed
-    __device__ __forceinline__ bool leaf(uint32_t g, bool active) {
-#ifdef ICP_LEAF_EAGER
-        const uint32_t before = bound_bits();
-        scan_leaf(pts, g, qx, qy, qz, b);
-        return __any_sync(0xffffffffu, active && bound_bits() != before);
-#else
-        return scan_leaf_lazy(pts, g, nq, active, b);
-#endif
-    }
+    __device__ __forceinline__ bool leaf(uint32_t g, bool active) { return scan_leaf_lazy<TRACK>(pts, g, nq, active, b, m2); }
 };
 
 // full exact 1-NN search of all lanes of a warp; each `b` may already hold a candidate (warm start).
 // Must be called by all 32 lanes; lanes without a query pass active = false.
-__device__ __forceinline__ void nn_traverse_warp(const TreeShape& sh, const WideNode* __restrict__ seg_nodes,
-                                                 const float4* __restrict__ seg_pts, float qx, float qy, float qz,
-                                                 bool active, uint32_t split_mask, Best& b) {
-    NNVisitor v{b, seg_pts, qx, qy, qz, make_neg_query(qx, qy, qz)};
+// Out-of-line entry of the walk: its own register allocation, so that the margin-tracking flavour (more live
+// state) does not tax the lean one when a kernel holds both.
+struct WalkResult { unsigned long long key; uint32_t m2; };
+template <bool TRACK>
+__device__ __forceinline__ uint32_t nn_traverse_warp(const TreeShape& sh, const WideNode* __restrict__ seg_nodes,
+                                                     const float4* __restrict__ seg_pts, float qx, float qy, float qz,
+                                                     bool active, uint32_t split_mask, Best& b);
+template <bool TRACK>
+__device__ __noinline__ WalkResult nn_walk(const TreeShape* sh, const WideNode* __restrict__ seg_nodes,
+                                           const float4* __restrict__ seg_pts, float qx, float qy, float qz, bool active,
+                                           unsigned long long key) {
+    Best b; b.key = key;
+    WalkResult r;
+    r.m2 = nn_traverse_warp<TRACK>(*sh, seg_nodes, seg_pts, qx, qy, qz, active, 0u, b);
+    r.key = b.key;
+    return r;
+}
+
+// Returns the lane's margin (see NNVisitor; TRACK = false: no margin, 0); a candidate already in `b` (seed) counts as seen.
+template <bool TRACK>
+__device__ __forceinline__ uint32_t nn_traverse_warp(const TreeShape& sh, const WideNode* __restrict__ seg_nodes,
+                                                     const float4* __restrict__ seg_pts, float qx, float qy, float qz,
+                                                     bool active, uint32_t split_mask, Best& b) {
+    NNVisitor<TRACK> v{b, seg_pts, qx, qy, qz, make_neg_query(qx, qy, qz), TRACK ? ICP_INF_BITS : 0u};
     wide_traverse_warp(sh, seg_nodes, qx, qy, qz, active, split_mask, v);
+    return v.m2;
 }
 
 // ---- k nearest ------------------------------------------------------------------------------
@@ -429,6 +489,8 @@ __device__ __forceinline__ void knn_offer_leaf(KList<KMAX, EXACT>& L, const floa
 // curve, which gives a finite first bound) and are skipped so that no candidate is parked twice.
 template <int KMAX, bool EXACT>
 struct KnnVisitor {
+    static constexpr bool kTrackMargin = false;
+    __device__ __forceinline__ void prune(uint32_t) {}
     KList<KMAX, EXACT>& L;
     const float4* __restrict__ pts;
     float qx, qy, qz;

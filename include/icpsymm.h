@@ -76,6 +76,10 @@ enum {
     ICPSYMM_OPT_MIN_NORMAL_DOT = 10, /* <= -1 = off; reject pairs whose normals disagree: n_p . n_q < value */
     ICPSYMM_OPT_TILE_ORDER = 12,    /* 1 (default) = hand the 256-query tiles of the first search out most expensive first (a cost
                                        estimate per tile); 0 = curve order.  Scheduling only: results are identical */
+    ICPSYMM_OPT_SKIP_WALK = 13,     /* 1 (default) = a 32-query unit whose nearest neighbours provably cannot have changed since its
+                                       last walk (each query moved by less than the gap between its neighbour and everything
+                                       else) keeps them without walking the index; 0 = always walk.
+                                       Results are identical either way */
     ICPSYMM_OPT_PEER_TIMEOUT_MS = 11, /* NVLink peer exchange: how long a rank waits for its peers' sums (default 10000 ms)
                                         before the call fails with ICPSYMM_ERR_COMM */
     ICPSYMM_OPT_ASYNC_SETUP = 9     /* 1 = set_source / set_target / estimate_normals return without waiting: each cloud is

@@ -299,6 +299,42 @@ def test_register_stream_mode_equals_graph_mode(ctx, cat, cat_out):
     assert np.array_equal(Tg, Tc) and sc["diff"] == sg["diff"]
 
 
+@pytest.mark.parametrize("case", ["cat", "synth200k", "noise_free"])
+def test_skipping_walks_never_changes_a_result(ctx, cat, cat_out, case):
+    """ICPSYMM_OPT_SKIP_WALK: a query whose winner provably stands keeps it without walking the index.  The proof is a
+    margin argument about fp32 values, so the result must be IDENTICAL to always walking: transform bits, diff, rmse,
+    iteration count and every correspondence of the last search -- and the walks must actually be skipped."""
+    if case == "cat":
+        src, tgt, thr, rel, iters = cat, cat_out, 1e-3, 0.0, 12
+    elif case == "synth200k":
+        src, tgt, _ = wl.config_synth(200_000)
+        thr, rel, iters = 1.0, 1e-7, 14          # runs on long after convergence: many skipped searches
+    else:
+        src, tgt, _ = wl.config_synth(60_000, noise_frac=0.0)
+        thr, rel, iters = 1e-9, 0.0, 10
+    ctx.set_source(src); ctx.set_target(tgt); ctx.estimate_normals(10)
+    ctx.set_option(icp.OPT_REL_DIFF_TOL, rel)
+    ctx.set_option(icp.OPT_KERNEL_TIMING, 1)
+    out = []
+    try:
+        for skip in (1, 0):
+            ctx.set_option(icp.OPT_SKIP_WALK, skip)
+            T, st, _ = ctx.register_symm(iters, thr)
+            idx, d2 = ctx.get_correspondences()
+            out.append((T.copy(), st, idx.copy(), d2.copy(), ctx.search_times()[0]))
+    finally:
+        ctx.set_option(icp.OPT_SKIP_WALK, 1)
+        ctx.set_option(icp.OPT_REL_DIFF_TOL, 0.0)
+        ctx.set_option(icp.OPT_KERNEL_TIMING, 0)
+    (Ta, sa, ia, da, ta), (Tb, sb, ib, db, tb) = out
+    assert np.array_equal(Ta, Tb) and np.array_equal(ia, ib) and np.array_equal(da, db)
+    assert sa["iters"] == sb["iters"] and sa["diff"] == sb["diff"] and sa["rmse"] == sb["rmse"] and sa["pairs"] == sb["pairs"]
+    oi, od = orc.KdTree(tgt).nn(orc.transform_points(Ta, src))
+    assert np.array_equal(ia, oi) and np.array_equal(da, od)
+    if case == "synth200k":
+        assert sa["searches"] >= 8 and ta[-1] < 0.6 * tb[-1], (ta, tb)   # the late searches are mostly skipped
+
+
 def test_register_identity_pairs_and_zero_trip(ctx, cat, cat_out, gold):
     ctx.set_source(cat); ctx.set_target(cat_out); ctx.estimate_normals(10)
     ctx.set_option(icp.OPT_IDENTITY_PAIRS, 1)
