@@ -101,6 +101,7 @@ void icpsymm_destroy(icpsymm_ctx* ctx) {
     cudaFree(ctx->trace_diff); cudaFree(ctx->io_buf); cudaFree(ctx->order_buf); cudaFree(ctx->order_temp);
     cudaFree(ctx->margin2); cudaFree(ctx->ref_search); cudaFree(ctx->hist);
     if (ctx->h_state) cudaFreeHost(ctx->h_state);
+    if (ctx->done_ev) cudaEventDestroy(ctx->done_ev);
     if (ctx->ev_begin) cudaEventDestroy(ctx->ev_begin);
     if (ctx->ev_end) cudaEventDestroy(ctx->ev_end);
     for (int i = 0; i < ctx->ev_pool_n; i++) cudaEventDestroy(ctx->ev_pool[i]);
@@ -199,6 +200,16 @@ int icpsymm_get_normals(icpsymm_ctx* ctx, int which, float* normals4) {
 int icpsymm_register_symm(icpsymm_ctx* ctx, int max_iters, float diff_threshold, float* T_out, icpsymm_stats* stats) {
     if (!ctx) return ICPSYMM_ERR_INVALID;
     return icp_run_loop(ctx, max_iters, diff_threshold, nullptr, nullptr, false, T_out, stats);
+}
+
+int icpsymm_register_symm_async(icpsymm_ctx* ctx, int max_iters, float diff_threshold) {
+    if (!ctx) return ICPSYMM_ERR_INVALID;
+    return icp_loop_enqueue(ctx, max_iters, diff_threshold, nullptr, nullptr, false);
+}
+
+int icpsymm_wait(icpsymm_ctx* ctx, float* T_out, icpsymm_stats* stats) {
+    if (!ctx) return ICPSYMM_ERR_INVALID;
+    return icp_loop_finish(ctx, T_out, stats);
 }
 
 int icpsymm_find_correspondences(icpsymm_ctx* ctx, const float T[16], int32_t* idx_out, float* d2_out) {

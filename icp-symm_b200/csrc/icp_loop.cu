@@ -43,11 +43,11 @@ struct K1Timer {
 };
 __device__ unsigned long long icp_k2_stamps[8];
 #define ICP_K2_STAMP(i) do { if (threadIdx.x == 0 && blockIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); icp_k2_stamps[i] = t_; } } while (0)
-extern "C" int icpsymm_debug_k2_stamps(unsigned long long* out) {
+extern "C" __attribute__((visibility("default"))) int icpsymm_debug_k2_stamps(unsigned long long* out) {
     cudaDeviceSynchronize();
     return (int)cudaMemcpyFromSymbol(out, icp_k2_stamps, sizeof(unsigned long long) * 8);
 }
-extern "C" int icpsymm_debug_k1_times(unsigned long long* out, int n) {
+extern "C" __attribute__((visibility("default"))) int icpsymm_debug_k1_times(unsigned long long* out, int n) {
     cudaDeviceSynchronize();
     return (int)cudaMemcpyFromSymbol(out, icp_k1_times, sizeof(unsigned long long) * 3 * n);
 }
@@ -57,7 +57,7 @@ extern "C" int icpsymm_debug_k1_times(unsigned long long* out, int n) {
 
 #ifdef ICP_TILE_TIMES   // developer instrumentation: start/end of every tile of the last K1 launch
 __device__ unsigned long long icp_tile_times[2 * 65536];
-extern "C" int icpsymm_debug_tile_times(unsigned long long* out, int n) {
+extern "C" __attribute__((visibility("default"))) int icpsymm_debug_tile_times(unsigned long long* out, int n) {
     cudaDeviceSynchronize();
     return (int)cudaMemcpyFromSymbol(out, icp_tile_times, sizeof(unsigned long long) * 2 * n);
 }
@@ -71,6 +71,10 @@ constexpr int kNNBlocksPerSM = 1024 / kNNThreads;   // 64 registers per thread: 
 #define ICP_TILES_PER_TICKET 1
 #endif
 constexpr int kTilesPerTicket = ICP_TILES_PER_TICKET;
+#ifndef ICP_TILES_PER_TICKET_SKIP
+#define ICP_TILES_PER_TICKET_SKIP 2
+#endif
+constexpr int kTilesPerTicketSkip = ICP_TILES_PER_TICKET_SKIP > ICP_TILES_PER_TICKET ? ICP_TILES_PER_TICKET_SKIP : ICP_TILES_PER_TICKET;
 #ifndef ICP_TRACK_STEP_SPACINGS
 #define ICP_TRACK_STEP_SPACINGS 4.0   // record margins once a step moves no point by more than this many point spacings
 #endif
@@ -233,7 +237,7 @@ __global__ void __launch_bounds__(kNNThreads, kNNBlocksPerSM) nn_accum_kernel(co
     __shared__ float sO[3];
     // the warps' fp32 totals; double-buffered by ticket parity: one barrier per ticket.  Kept small on purpose: shared
     // memory comes out of the SM's L1 (4 blocks x this), and the walk lives on its L1 hit rate
-    __shared__ float wacc[2][kTilesPerTicket][kNNWarps][ICP_PART_STRIDE];
+    __shared__ float wacc[2][kTilesPerTicketSkip][kNNWarps][ICP_PART_STRIDE];
     __shared__ int sDone;
     __shared__ uint32_t sSearch;      // index of the running search of the block's current pair
     __shared__ int sTrack;            // walks of this search record margins (K2 expects the next step to be small)
@@ -245,10 +249,11 @@ __global__ void __launch_bounds__(kNNThreads, kNNBlocksPerSM) nn_accum_kernel(co
     // at the start of the current one, so the latency of the atomic hides behind the tile's work
     uint32_t w = blockIdx.x;
     const bool use_order = P.order != nullptr && P.state[0].searches == 0;   // the order is made for the first search
-    // a ticket is one tile in the ordered first search (fine grain: its tiles differ 20x in cost) and two
-    // neighbouring tiles otherwise: a warp then takes its unit of the first and of the second tile without a
-    // barrier in between, which halves the time warps wait for the slowest of the eight
-    const uint32_t tpt = use_order ? 1u : (uint32_t)kTilesPerTicket;
+    // a ticket is one tile while the searches walk (fine grain: the tiles of a far search differ 20x in cost; two
+    // tiles per ticket measured 4-5 % slower even near convergence), and two once margins exist (K1 skip test): most warps then only re-check their winners (a few dependent
+    // loads) while one or two of the eight walk, and with one tile per barrier the block spends its time waiting --
+    // ncu: barrier stall 6-7 cycles per instruction, issue slots 40 % busy.  (launch-uniform: every block reads pair 0)
+    const uint32_t tpt = use_order ? 1u : (P.state[0].have_margins ? (uint32_t)kTilesPerTicketSkip : (uint32_t)kTilesPerTicket);
     const uint32_t tickets_per_seg = (P.work_per_seg + tpt - 1u) / tpt;
     const uint32_t total_tickets = (P.total_work / P.work_per_seg) * tickets_per_seg;
     for (uint32_t it = 0; w < total_tickets; it++) {
@@ -897,6 +902,15 @@ static void launch_iteration(icpsymm_ctx* ctx, const NNParams& np, SolveParams s
 
 int icp_run_loop(icpsymm_ctx* ctx, int max_iters, float thr, const float* T_init, const double* origin,
                  bool single_search, float* T_out, icpsymm_stats* stats) {
+    int rc = icp_loop_enqueue(ctx, max_iters, thr, T_init, origin, single_search);
+    if (rc < 0) return rc;
+    return icp_loop_finish(ctx, T_out, stats);
+}
+
+// first half of a registration: everything is ENQUEUED on the context stream, nothing waits for the device
+int icp_loop_enqueue(icpsymm_ctx* ctx, int max_iters, float thr, const float* T_init, const double* origin,
+                     bool single_search) {
+    if (ctx->pending.active) return icp_fail_msg(ctx, ICPSYMM_ERR_INVALID, "a registration is already in flight: call icpsymm_wait first");
     CloudSet& S = ctx->src;
     CloudSet& T = ctx->tgt;
     { int jr = icp_join_clouds(ctx, true); if (jr < 0) return jr; }   // asynchronous setup: join + deferred checks
@@ -1101,8 +1115,26 @@ int icp_run_loop(icpsymm_ctx* ctx, int max_iters, float thr, const float* T_init
     }
     ICP_CUDA_CHECK(cudaGetLastError());
     ICP_CUDA_CHECK(cudaMemcpyAsync(ctx->h_state, ctx->d_state, sizeof(SegState) * nseg, cudaMemcpyDeviceToHost, st));
-    ICP_CUDA_CHECK(cudaStreamSynchronize(st));
+    if (!ctx->done_ev) ICP_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->done_ev, cudaEventDisableTiming));
+    ICP_CUDA_CHECK(cudaEventRecord(ctx->done_ev, st));
     ctx->have_corr = true;
+    // everything the second half needs to turn the pinned state into the caller's outputs
+    ctx->pending.active = true; ctx->pending.nseg = nseg; ctx->pending.n_search = n_search; ctx->pending.timing = timing;
+    ctx->pending.use_comm = use_comm; ctx->pending.single_search = single_search; ctx->pending.part0 = part0;
+    ctx->pending.nparts = nparts;
+    return ICPSYMM_OK;
+}
+
+// second half of a registration: wait for the loop enqueued by icp_loop_enqueue and hand out its result
+int icp_loop_finish(icpsymm_ctx* ctx, float* T_out, icpsymm_stats* stats) {
+    if (!ctx->pending.active) return icp_fail_msg(ctx, ICPSYMM_ERR_NOT_READY, "no registration in flight");
+    ctx->pending.active = false;
+    CloudSet& S = ctx->src;
+    cudaStream_t st = ctx->stream;
+    const uint32_t nseg = ctx->pending.nseg, part0 = ctx->pending.part0, nparts = ctx->pending.nparts;
+    const int n_search = ctx->pending.n_search;
+    const bool timing = ctx->pending.timing, use_comm = ctx->pending.use_comm, single_search = ctx->pending.single_search;
+    ICP_CUDA_CHECK(cudaEventSynchronize(ctx->done_ev));
     if (ctx->peer_world > 1) {
         LoopCtrl hc;
         ICP_CUDA_CHECK(cudaMemcpy(&hc, ctx->d_ctrl, sizeof hc, cudaMemcpyDeviceToHost));
@@ -1275,7 +1307,7 @@ __global__ void seed_kernel(const uint32_t* __restrict__ in, uint32_t* __restric
     out[i] = mode == 0 ? 0xffffffffu : in[j];
 }
 }
-extern "C" int icpsymm_debug_seed(icpsymm_ctx* ctx, int mode) {
+extern "C" __attribute__((visibility("default"))) int icpsymm_debug_seed(icpsymm_ctx* ctx, int mode) {
     // mode -1: back up the current correspondences; mode >= 0: corr = f_mode(backup)
     static uint32_t* backup = nullptr; static size_t cap = 0;
     const size_t n = (size_t)ctx->src.shape.pitch;
@@ -1285,7 +1317,7 @@ extern "C" int icpsymm_debug_seed(icpsymm_ctx* ctx, int mode) {
     ctx->have_corr = true;
     return (int)cudaGetLastError();
 }
-extern "C" int icpsymm_debug_single_search(icpsymm_ctx* ctx, const float* T16, icpsymm_stats* stats) {
+extern "C" __attribute__((visibility("default"))) int icpsymm_debug_single_search(icpsymm_ctx* ctx, const float* T16, icpsymm_stats* stats) {
     return icp_run_single(ctx, T16, nullptr, stats);
 }
 #endif

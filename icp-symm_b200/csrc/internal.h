@@ -119,6 +119,14 @@ struct icpsymm_ctx {
     cudaGraphExec_t graph_exec = nullptr;
     GraphKey graph_key;
 
+    // a registration whose loop has been enqueued but whose result has not been handed out yet
+    struct Pending {
+        bool active = false, timing = false, use_comm = false, single_search = false;
+        uint32_t nseg = 0, part0 = 0, nparts = ICP_NPARTS;
+        int n_search = 0;
+    } pending;
+    cudaEvent_t done_ev = nullptr;
+
     // timing
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
     cudaEvent_t* ev_pool = nullptr; int ev_pool_n = 0; int timed_searches = 0;
@@ -159,6 +167,8 @@ int icp_import_normals(icpsymm_ctx* ctx, CloudSet& cs, const float* in_host);
 // icp_loop.cu
 int icp_run_loop(icpsymm_ctx* ctx, int max_iters, float thr, const float* T_init /*12 floats (3x4) or null*/,
                  const double* origin /*3 or null*/, bool single_search, float* T_out, icpsymm_stats* stats);
+int icp_loop_enqueue(icpsymm_ctx* ctx, int max_iters, float thr, const float* T_init, const double* origin, bool single_search);
+int icp_loop_finish(icpsymm_ctx* ctx, float* T_out, icpsymm_stats* stats);
 int icp_run_single(icpsymm_ctx* ctx, const float* T16, const double* origin, icpsymm_stats* stats);
 int icp_export_correspondences(icpsymm_ctx* ctx, int32_t* idx_out, float* d2_out);
 int icp_export_transformed(icpsymm_ctx* ctx, const float* T, float* xyz_out, size_t stride_bytes);

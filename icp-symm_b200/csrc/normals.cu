@@ -26,17 +26,17 @@ struct BlockTimer {
         }
     }
 };
-extern "C" int icpsymm_debug_sorted_points(icpsymm_ctx* ctx, int which, float* out, size_t n) {
+extern "C" __attribute__((visibility("default"))) int icpsymm_debug_sorted_points(icpsymm_ctx* ctx, int which, float* out, size_t n) {
     cudaDeviceSynchronize();
     const CloudSet& cs = which ? ctx->tgt : ctx->src;
     return (int)cudaMemcpy(out, cs.pts, n * sizeof(float4), cudaMemcpyDeviceToHost);
 }
-extern "C" int icpsymm_debug_unit_split(icpsymm_ctx* ctx, int which, uint32_t* out, size_t n) {
+extern "C" __attribute__((visibility("default"))) int icpsymm_debug_unit_split(icpsymm_ctx* ctx, int which, uint32_t* out, size_t n) {
     cudaDeviceSynchronize();
     const CloudSet& cs = which ? ctx->tgt : ctx->src;
     return (int)cudaMemcpy(out, cs.unit_split, n * sizeof(uint32_t), cudaMemcpyDeviceToHost);
 }
-extern "C" int icpsymm_debug_block_times(unsigned long long* out, int n) {
+extern "C" __attribute__((visibility("default"))) int icpsymm_debug_block_times(unsigned long long* out, int n) {
     cudaDeviceSynchronize();
     return (int)cudaMemcpyFromSymbol(out, icp_blk_times, sizeof(unsigned long long) * 3 * n);
 }

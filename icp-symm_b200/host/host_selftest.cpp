@@ -52,6 +52,34 @@ int main(int argc, char** argv) {
         fclose(f);
         CHECK(loadPCDFile(path, bad) != 0);                      // truncated file
     }
+    // hostile or unsupported headers come back as error codes: no exception, no giant allocation, no zeros
+    {
+        const char* hdrs[] = {
+            "VERSION 0.7\nFIELDS x y z\nSIZE 4 4 4\nTYPE F F F\nCOUNT 1 1 1\nWIDTH 1\nHEIGHT 1\nPOINTS 18446744073709551615\nDATA ascii\n1 2 3\n",
+            "VERSION 0.7\nFIELDS x y z\nSIZE 4 4 4\nTYPE F F F\nCOUNT 1 1 1\nWIDTH 4000000000\nHEIGHT 4000000000\nDATA binary\n",
+            "VERSION 0.7\nFIELDS x y z\nSIZE -4 4 4\nTYPE F F F\nCOUNT 1 1 1\nWIDTH 1\nHEIGHT 1\nPOINTS 1\nDATA ascii\n1 2 3\n",
+            "VERSION 0.7\nFIELDS x y z\nSIZE 4 4 4\nTYPE F F F\nCOUNT 0 1 1\nWIDTH 1\nHEIGHT 1\nPOINTS 1\nDATA ascii\n1 2 3\n",
+            "VERSION 0.7\nFIELDS x y z\nSIZE 2 2 2\nTYPE F F F\nCOUNT 1 1 1\nWIDTH 1\nHEIGHT 1\nPOINTS 1\nDATA binary\nabcdef",
+            "VERSION 0.7\nFIELDS x y z\nSIZE 4 4 4\nTYPE Q F F\nCOUNT 1 1 1\nWIDTH 1\nHEIGHT 1\nPOINTS 1\nDATA ascii\n1 2 3\n",
+        };
+        for (const char* h : hdrs) {
+            std::string path = dir + "/selftest_bad.pcd";
+            FILE* f = fopen(path.c_str(), "wb");
+            fputs(h, f);
+            fclose(f);
+            PointCloud<PointXYZ> r;
+            CHECK(loadPCDFile(path, r) < 0);
+        }
+        // 8-byte fields are part of the format: double coordinates load as values, not as zeros
+        std::string path = dir + "/selftest_f8.pcd";
+        FILE* f = fopen(path.c_str(), "wb");
+        fputs("VERSION 0.7\nFIELDS x y z\nSIZE 8 8 8\nTYPE F F F\nCOUNT 1 1 1\nWIDTH 1\nHEIGHT 1\nPOINTS 1\nDATA binary\n", f);
+        const double xyz[3] = {1.5, -2.25, 3.0};
+        fwrite(xyz, 8, 3, f);
+        fclose(f);
+        PointCloud<PointXYZ> r;
+        CHECK(loadPCDFile(path, r) == 0 && r.points.size() == 1 && r.points[0].x == 1.5f && r.points[0].y == -2.25f);
+    }
     {
         std::string path = dir + "/selftest_za.txt";
         FILE* f = fopen(path.c_str(), "w");

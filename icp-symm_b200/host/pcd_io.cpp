@@ -16,6 +16,13 @@ struct Field {
     size_t offset = 0;
 };
 
+// the encodings the PCD format defines: F4 F8, I1 I2 I4 I8, U1 U2 U4 U8
+bool supported(const Field& f) {
+    if (f.type == 'F') return f.size == 4 || f.size == 8;
+    if (f.type == 'I' || f.type == 'U') return f.size == 1 || f.size == 2 || f.size == 4 || f.size == 8;
+    return false;
+}
+
 double read_scalar(const char* p, const Field& f) {
     switch (f.type) {
         case 'F':
@@ -26,14 +33,16 @@ double read_scalar(const char* p, const Field& f) {
             if (f.size == 1) { uint8_t v; memcpy(&v, p, 1); return v; }
             if (f.size == 2) { uint16_t v; memcpy(&v, p, 2); return v; }
             if (f.size == 4) { uint32_t v; memcpy(&v, p, 4); return v; }
+            if (f.size == 8) { uint64_t v; memcpy(&v, p, 8); return (double)v; }
             break;
         case 'I':
             if (f.size == 1) { int8_t v; memcpy(&v, p, 1); return v; }
             if (f.size == 2) { int16_t v; memcpy(&v, p, 2); return v; }
             if (f.size == 4) { int32_t v; memcpy(&v, p, 4); return v; }
+            if (f.size == 8) { int64_t v; memcpy(&v, p, 8); return (double)v; }
             break;
     }
-    return 0.0;
+    return 0.0;   // unreachable: loadPCDFile rejects every other encoding (-6)
 }
 }  // namespace
 
@@ -72,7 +81,29 @@ int loadPCDFile(const std::string& path, PointCloud<PointXYZ>& cloud, PointCloud
         }
     }
     if (fields.empty() || data_kind.empty()) return -2;
-    if (!have_points) npts = width * height;
+    if (!in) return -2;
+    // the header is untrusted input: reject what the format does not define instead of wrapping sizes or
+    // reading unsupported encodings as zeros (MyICP::LoadCloud returns these codes, it never throws)
+    for (const auto& f : fields)
+        if (f.count < 1 || f.count > 4096 || !supported(f)) return -6;
+    if (!have_points) {
+        if (height != 0 && width > (size_t)-1 / height) return -6;
+        npts = width * height;
+    }
+    {
+        // a point needs at least one byte per field (binary) or two characters per column (ascii): bound npts by
+        // the bytes that are actually left in the file before allocating anything
+        const std::streampos here = in.tellg();
+        in.seekg(0, std::ios::end);
+        const std::streampos end = in.tellg();
+        in.seekg(here);
+        if (here < 0 || end < here) return -2;
+        const size_t left = (size_t)(end - here);
+        size_t rec = 0;
+        for (const auto& f : fields) rec += (size_t)f.size * (size_t)f.count;
+        const size_t min_bytes = data_kind == "binary" ? rec : 2 * fields.size() - 1;
+        if (min_bytes == 0 || npts > left / min_bytes) return -4;
+    }
     int ix = -1, iy = -1, iz = -1, inx = -1, iny = -1, inz = -1, icv = -1;
     size_t off = 0, ncols = 0;
     for (size_t i = 0; i < fields.size(); i++) {

@@ -71,6 +71,8 @@ def load():
         "icpsymm_set_normals": (C.c_int, [vp, C.c_int, fp]),
         "icpsymm_get_normals": (C.c_int, [vp, C.c_int, fp]),
         "icpsymm_register_symm": (C.c_int, [vp, C.c_int, C.c_float, fp, C.POINTER(Stats)]),
+        "icpsymm_register_symm_async": (C.c_int, [vp, C.c_int, C.c_float]),
+        "icpsymm_wait": (C.c_int, [vp, fp, C.POINTER(Stats)]),
         "icpsymm_find_correspondences": (C.c_int, [vp, fp, ip, fp]),
         "icpsymm_get_correspondences": (C.c_int, [vp, ip, fp]),
         "icpsymm_eval_diff": (C.c_int, [vp, fp, dp]),
@@ -260,6 +262,19 @@ class Context:
         T = np.empty((self.n_pairs, 16), np.float32)
         st = (Stats * self.n_pairs)()
         rc = self._check(self.L.icpsymm_register_symm(self.h, max_iters, diff_threshold, _fp(T), st))
+        stats = [s.as_dict() for s in st]
+        if self.n_pairs == 1:
+            return T.reshape(4, 4), stats[0], rc
+        return T.reshape(-1, 4, 4), stats, rc
+
+    def register_symm_async(self, max_iters=10, diff_threshold=1.0):
+        """enqueue the loop and return; wait() hands out the result"""
+        self._check(self.L.icpsymm_register_symm_async(self.h, max_iters, diff_threshold))
+
+    def wait(self):
+        T = np.empty((self.n_pairs, 16), np.float32)
+        st = (Stats * self.n_pairs)()
+        rc = self._check(self.L.icpsymm_wait(self.h, _fp(T), st))
         stats = [s.as_dict() for s in st]
         if self.n_pairs == 1:
             return T.reshape(4, 4), stats[0], rc

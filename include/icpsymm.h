@@ -28,6 +28,9 @@
 #ifdef __cplusplus
 extern "C" {
 #endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)   /* the library is built with -fvisibility=hidden: only this header is exported */
+#endif
 
 #define ICPSYMM_OK 0
 #define ICPSYMM_WARN_DEGENERATE 1    /* a 6x6 pivot was dropped (rank-deficient geometry) */
@@ -130,6 +133,14 @@ int icpsymm_get_normals(icpsymm_ctx* ctx, int which, float* normals4);
 int icpsymm_register_symm(icpsymm_ctx* ctx, int max_iters, float diff_threshold, float* T_out,
                           icpsymm_stats* stats);
 
+/* The same registration in two halves, for callers that pipeline pairs: _async ENQUEUES the whole loop on the context's
+ * stream and returns without waiting for the device; icpsymm_wait blocks until it is done and hands out what
+ * icpsymm_register_symm would have returned.  With ICPSYMM_OPT_ASYNC_SETUP the set-up calls do not block either, so one
+ * host thread can upload, index and start pair k+1 on a second context while pair k is still iterating on the first.
+ * Exactly one registration may be in flight per context; any other call on that context must come after icpsymm_wait. */
+int icpsymm_register_symm_async(icpsymm_ctx* ctx, int max_iters, float diff_threshold);
+int icpsymm_wait(icpsymm_ctx* ctx, float* T_out, icpsymm_stats* stats);
+
 /* ---- building blocks of the loop, exposed because the reference exposes them (func.h:5-27) ---- */
 /* the missing search of myicp.cpp:128-131: exact 1-NN of T*source in target, lowest index on ties.
  * idx_out: n_source int32 (original target indices), d2_out (optional): fp32 squared distances. */
@@ -182,6 +193,9 @@ int icpsymm_peer_export(icpsymm_ctx* ctx, void* handle64_out);
 int icpsymm_peer_attach(icpsymm_ctx* ctx, const void* handles /* n_ranks x 64 bytes */, int n_ranks, int rank);
 int icpsymm_peer_detach(icpsymm_ctx* ctx);
 
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
 #ifdef __cplusplus
 }
 #endif

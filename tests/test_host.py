@@ -31,6 +31,17 @@ def test_library_exports_every_declared_symbol(built):
     assert set(declared) == set(built.declared_symbols())
 
 
+def test_release_library_exports_nothing_but_the_header(built):
+    """developer instrumentation (ICP_BLOCK_TIMES, ICP_TILE_TIMES, ICP_EXPERIMENT) must not leak into the shipped library:
+    its dynamic symbol table holds exactly the icpsymm_* entry points of include/icpsymm.h"""
+    out = subprocess.run(["nm", "-D", "--defined-only", os.path.join(PKG, "libicpsymm_b200.so")], capture_output=True, text=True)
+    assert out.returncode == 0
+    exported = {ln.split()[-1] for ln in out.stdout.splitlines() if " T " in ln}
+    ours = {s for s in exported if "icp" in s.lower() and not s.startswith("_Z")}
+    assert ours == set(built.declared_symbols()), sorted(ours ^ set(built.declared_symbols()))
+    assert not any("debug" in s for s in exported)
+
+
 def test_header_cites_the_reference_interfaces():
     hdr = open(os.path.join(ROOT, "include", "icpsymm.h")).read()
     for cite in ("myicp.h:7-36", "regist.h:8", "myicp.cpp:100-150", "myicp.cpp:152-172", "func.cpp:43-60"):

@@ -182,6 +182,16 @@ def test_solve_compose_matches_independent_lstsq_golden(cat, cat_out, gold, solv
     assert wl.rotation_angle(solve_gold["T_identity"], gold["truth_R"]) < 1e-7
 
 
+def test_distance_between_canonical_and_literal_loops_is_pinned(cat, cat_out, gold):
+    """what a drop-in user sees differently from upstream, as numbers that must not drift"""
+    ns, nt = gold["normals_cat"], gold["normals_cat_out"]
+    r = orc.register_symm(cat, ns, cat_out, nt, max_iters=1, diff_threshold=1.0, identity_pairs=True)
+    assert r["iters"] == 1 and wl.rotation_angle(r["T"], gold["truth_R"]) < 1e-6
+    assert wl.rotation_angle(r["T"], gold["lit_T1"]) == pytest.approx(0.1066, abs=2e-3)
+    assert wl.rotation_angle(gold["lit_T_final"], gold["truth_R"]) == pytest.approx(2.07e-3, abs=2e-4)
+    assert gold["lit_diffs"][-1] > 2.7e4 and len(gold["lit_diffs"]) == 11        # the literal loop never meets diff <= 1
+
+
 def test_accumulate_matches_literal_rows_and_recentring(cat, cat_out, gold):
     """sum of Oracle-L rows (func.cpp:43-60) == Oracle-C raw sums about origin 0; re-centring is exact algebra."""
     ns, nt = gold["normals_cat"], gold["normals_cat_out"]
