@@ -271,6 +271,11 @@ int icpsymm_get_trace(icpsymm_ctx* ctx, size_t pair, int k, float T[16], double*
     return ICPSYMM_OK;
 }
 
+int icpsymm_register_p2p(icpsymm_ctx* ctx, int max_iters, float diff_threshold, float* T_out, icpsymm_stats* stats) {
+    if (!ctx) return ICPSYMM_ERR_INVALID;
+    return icp_register_p2p(ctx, max_iters, diff_threshold, T_out, stats);
+}
+
 int icpsymm_get_search_times(icpsymm_ctx* ctx, float* search_ms, float* solve_ms, int n) {
     if (!ctx || n < 0) return ICPSYMM_ERR_INVALID;
     return icp_search_times(ctx, search_ms, solve_ms, n);

@@ -176,46 +176,59 @@ __global__ void init_state_kernel(SegState* state, uint32_t nseg, InitArgs a, co
 // the number of boxes of that level within r -- and the tiles are handed out most expensive first
 // (stable radix sort: equal costs keep curve order, so neighbouring blocks still share lines).
 // ------------------------------------------------------------------------------------------------
+constexpr int kCostBoxesMax = 4096;   // boxes of the coarse level staged in shared memory (96 KB)
 __global__ void __launch_bounds__(256) tile_cost_kernel(CloudView src, CloudView tgt, const SegState* __restrict__ state,
                                                         uint32_t part0, uint32_t nparts, uint32_t work, int rec_level,
-                                                        uint32_t* __restrict__ key_out, uint32_t* __restrict__ val_out) {
-    const uint32_t wid = (blockIdx.x * 256u + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
-    if (wid >= work) return;
-    const uint32_t ns = src.counts[0], tiles = icp_tiles(ns);
-    const uint32_t tile = icp_part_tile_lo(tiles, part0) + wid;
-    uint32_t cost = 0u;
-    if (tile < icp_part_tile_lo(tiles, part0 + nparts) && tgt.counts[0] > 0) {
-        uint32_t i = tile * ICP_TILE + ICP_TILE / 2;
-        if (i >= ns) i = ns - 1;
-        const float4 sp = ldg4(src.pts + i);
-        const float3 q = apply_rn(state[0].Tf, sp.x, sp.y, sp.z);
-        const WideNode* recs = tgt.nodes + tgt.shape.level_off[rec_level];
-        const uint32_t nbox = tgt.shape.level_cnt[rec_level] * ICP_FAN;
-        float r2 = __int_as_float(0x7f800000);
-        for (uint32_t b = lane; b < nbox; b += 32u) {
-            const WideNode* nd = recs + (b >> ICP_LOG_FAN);
-            const int c = b & (ICP_FAN - 1);
-            const float lx = nd->lox[c], ly = nd->loy[c], lz = nd->loz[c], hx = nd->hix[c], hy = nd->hiy[c], hz = nd->hiz[c];
-            if (lx <= hx) {   // not a padding box
-                const float fx = fmaxf(fabsf(q.x - lx), fabsf(q.x - hx)), fy = fmaxf(fabsf(q.y - ly), fabsf(q.y - hy));
-                const float fz = fmaxf(fabsf(q.z - lz), fabsf(q.z - hz));
-                r2 = fminf(r2, fx * fx + fy * fy + fz * fz);
-            }
+                                                        uint32_t tiles_per_warp, uint32_t* __restrict__ key_out,
+                                                        uint32_t* __restrict__ val_out) {
+    // the boxes of the coarse level, once per block: [6][nbox] floats (lo xyz, hi xyz); padding boxes have lo > hi
+    extern __shared__ float sbox[];
+    const uint32_t nbox = min(tgt.shape.level_cnt[rec_level] * ICP_FAN, (uint32_t)kCostBoxesMax);
+    {
+        const float* recs = reinterpret_cast<const float*>(tgt.nodes + tgt.shape.level_off[rec_level]);
+        for (uint32_t t = threadIdx.x; t < nbox * 6u; t += 256u) {
+            // record r holds 48 floats: lox[8] loy[8] loz[8] hix[8] hiy[8] hiz[8]
+            const uint32_t r = t / 48u, k = (t % 48u) / 8u, c = t % 8u;
+            sbox[k * nbox + r * 8u + c] = __ldg(recs + t);
         }
-        r2 = warp_min_f(r2);
-        for (uint32_t b = lane; b < nbox; b += 32u) {
-            const WideNode* nd = recs + (b >> ICP_LOG_FAN);
-            const int c = b & (ICP_FAN - 1);
-            const float lx = nd->lox[c], ly = nd->loy[c], lz = nd->loz[c], hx = nd->hix[c], hy = nd->hiy[c], hz = nd->hiz[c];
-            const float ex = fmaxf(fmaxf(lx - q.x, q.x - hx), 0.f), ey = fmaxf(fmaxf(ly - q.y, q.y - hy), 0.f);
-            const float ez = fmaxf(fmaxf(lz - q.z, q.z - hz), 0.f);
-            cost += (lx <= hx && ex * ex + ey * ey + ez * ez <= r2) ? 1u : 0u;
-        }
-        cost = __reduce_add_sync(0xffffffffu, cost);
     }
-    if (lane == 0) {
-        key_out[wid] = 0xffffu - (cost > 0xffffu ? 0xffffu : cost);   // ascending key = descending cost
-        val_out[wid] = wid;
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31u, warp_global = (blockIdx.x * 256u + threadIdx.x) >> 5;
+    const uint32_t ns = src.counts[0], tiles = icp_tiles(ns);
+    const float *blx = sbox, *bly = sbox + nbox, *blz = sbox + 2 * nbox, *bhx = sbox + 3 * nbox, *bhy = sbox + 4 * nbox,
+                *bhz = sbox + 5 * nbox;
+    for (uint32_t k = 0; k < tiles_per_warp; k++) {
+        const uint32_t wid = warp_global * tiles_per_warp + k;
+        if (wid >= work) return;
+        const uint32_t tile = icp_part_tile_lo(tiles, part0) + wid;
+        uint32_t cost = 0u;
+        if (tile < icp_part_tile_lo(tiles, part0 + nparts) && tgt.counts[0] > 0) {
+            uint32_t i = tile * ICP_TILE + ICP_TILE / 2;
+            if (i >= ns) i = ns - 1;
+            const float4 sp = ldg4(src.pts + i);
+            const float3 q = apply_rn(state[0].Tf, sp.x, sp.y, sp.z);
+            float r2 = __int_as_float(0x7f800000);
+            for (uint32_t b = lane; b < nbox; b += 32u) {
+                const float lx = blx[b], ly = bly[b], lz = blz[b], hx = bhx[b], hy = bhy[b], hz = bhz[b];
+                if (lx <= hx) {   // not a padding box
+                    const float fx = fmaxf(fabsf(q.x - lx), fabsf(q.x - hx)), fy = fmaxf(fabsf(q.y - ly), fabsf(q.y - hy));
+                    const float fz = fmaxf(fabsf(q.z - lz), fabsf(q.z - hz));
+                    r2 = fminf(r2, fx * fx + fy * fy + fz * fz);
+                }
+            }
+            r2 = warp_min_f(r2);
+            for (uint32_t b = lane; b < nbox; b += 32u) {
+                const float lx = blx[b], ly = bly[b], lz = blz[b], hx = bhx[b], hy = bhy[b], hz = bhz[b];
+                const float ex = fmaxf(fmaxf(lx - q.x, q.x - hx), 0.f), ey = fmaxf(fmaxf(ly - q.y, q.y - hy), 0.f);
+                const float ez = fmaxf(fmaxf(lz - q.z, q.z - hz), 0.f);
+                cost += (lx <= hx && ex * ex + ey * ey + ez * ez <= r2) ? 1u : 0u;
+            }
+            cost = __reduce_add_sync(0xffffffffu, cost);
+        }
+        if (lane == 0) {
+            key_out[wid] = 0xffffu - (cost > 0xffffu ? 0xffffu : cost);   // ascending key = descending cost
+            val_out[wid] = wid;
+        }
     }
 }
 
@@ -1027,9 +1040,9 @@ int icp_loop_enqueue(icpsymm_ctx* ctx, int max_iters, float thr, const float* T_
     // most-expensive-first order of the first search (single pairs that fill the machine more than twice)
     if (nseg == 1 && !ctx->opt_identity && ctx->opt_tile_order && np.total_work >= 2u * np.grid && T.shape.n_levels >= 4) {
         const uint32_t work = np.total_work;
-        int rec_level = 1;   // records of level l hold the boxes of level l-1: the coarsest level with at least 1024 boxes
-        for (uint32_t l = T.shape.n_levels - 1; l >= 1; l--)
-            if (T.shape.level_cnt[l] * ICP_FAN >= 1024u || l == 1) { rec_level = (int)l; break; }
+        int rec_level = (int)T.shape.n_levels - 1;   // records of level l hold the boxes of level l-1: the finest level
+        for (uint32_t l = 1; l + 1 <= T.shape.n_levels - 1; l++)   // whose boxes fit the kernel's shared memory
+            if (T.shape.level_cnt[l] * ICP_FAN <= (uint32_t)kCostBoxesMax) { rec_level = (int)l; break; }
         size_t cap = ctx->order_cap;
         if ((rc = icp_reserve(ctx, &ctx->order_buf, &cap, (size_t)4 * work))) return rc;
         ctx->order_cap = cap;
@@ -1041,8 +1054,17 @@ int icp_loop_enqueue(icpsymm_ctx* ctx, int max_iters, float thr, const float* T_
             if ((rc = icp_reserve(ctx, &tmp, &ctx->order_temp_bytes, temp_bytes))) return rc;
             ctx->order_temp = tmp;
         }
-        tile_cost_kernel<<<(work * 32u + 255u) / 256u, 256, 0, st>>>(S.view(), T.view(), ctx->d_state, part0, nparts, work,
-                                                                      rec_level, ka, va);
+        {
+            // one warp per 4 tiles: enough blocks to fill the machine, few enough to amortise the staging of the boxes
+            const uint32_t tpw = work >= 16384u ? 16u : 4u, warps = (work + tpw - 1u) / tpw;
+            const size_t smem = (size_t)kCostBoxesMax * 6 * sizeof(float);
+            if (!ctx->cost_attr_set) {   // per device
+                ICP_CUDA_CHECK(cudaFuncSetAttribute(tile_cost_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                ctx->cost_attr_set = true;
+            }
+            tile_cost_kernel<<<(warps * 32u + 255u) / 256u, 256, smem, st>>>(S.view(), T.view(), ctx->d_state, part0, nparts,
+                                                                             work, rec_level, tpw, ka, va);
+        }
         ICP_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(ctx->order_temp, temp_bytes, ka, kb, va, vb, (int)work, 0, 16, st));
         np.order = vb;
     }

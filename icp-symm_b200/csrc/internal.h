@@ -97,6 +97,7 @@ struct icpsymm_ctx {
     void* io_buf = nullptr;       size_t io_bytes = 0;   // device scratch for exports/imports
     uint32_t* order_buf = nullptr; size_t order_cap = 0;  // tile order of the first search: keys/values, double-buffered
     void* order_temp = nullptr;   size_t order_temp_bytes = 0;
+    bool cost_attr_set = false;
     bool have_corr = false;
 
     // options
@@ -179,6 +180,7 @@ int icp_search_times(icpsymm_ctx* ctx, float* search_ms, float* solve_ms, int n)
 
 // kabsch.cu
 int icp_kabsch(icpsymm_ctx* ctx, const double* src, const double* dst, size_t n, double R[9], double T[3]);
+int icp_register_p2p(icpsymm_ctx* ctx, int max_iters, float thr, float* T_out, icpsymm_stats* stats);
 
 // comm.cu
 int icp_comm_allreduce(icpsymm_ctx* ctx, double* buf, size_t count);

@@ -5,6 +5,8 @@
 // T = dstbar - R srcbar (:64-69); net effect dst = R src + T.  Here: two deterministic
 // block-partial reductions (centroids, then the centred 3x3 cross-covariance) and a one-thread
 // one-sided Jacobi SVD of the 3x3.
+#include <cstring>
+
 #include "internal.h"
 
 namespace {
@@ -155,7 +157,91 @@ __global__ void kabsch_solve_kernel(const double* __restrict__ partial, int nblo
         out[9 + r] = mean[3 + r] - (R[3 * r] * mean[0] + R[3 * r + 1] * mean[1] + R[3 * r + 2] * mean[2]);
 }
 
+// pairs of the point-to-point loop, straight from the context's device state: (T p_j, target point matched to p_j)
+// for every sorted source position j, as the fp64 arrays the reduction kernels read
+struct T12f { float m[12]; };
+__global__ void __launch_bounds__(256) p2p_pairs_kernel(CloudView src, CloudView tgt, const uint32_t* __restrict__ corr,
+                                                        T12f T, double* __restrict__ a, double* __restrict__ b) {
+    const uint32_t j = blockIdx.x * 256u + threadIdx.x;
+    if (j >= src.counts[0]) return;
+    const float4 s = src.pts[j];
+    const float3 p = apply_rn(T.m, s.x, s.y, s.z);
+    const uint32_t pos = corr[j];
+    const float4 q = tgt.pts[pos < tgt.counts[0] ? pos : 0];
+    a[3 * (size_t)j] = p.x; a[3 * (size_t)j + 1] = p.y; a[3 * (size_t)j + 2] = p.z;
+    b[3 * (size_t)j] = q.x; b[3 * (size_t)j + 1] = q.y; b[3 * (size_t)j + 2] = q.z;
+}
+
 }  // namespace
+
+// Point-to-point ICP, the loop MyICP::RegisterP2P stands for (the reference's is a stub that applies an identity guess,
+// myicp.cpp:43-59): exact correspondences (K1), closed-form fit of the matched pairs (registrateNPoint, regist.h:8-72),
+// transform = incre * transform, until diff <= threshold or max_iters (the loop shape of myicp.cpp:121-142).
+// Everything stays on the device; per iteration the host reads back one diff and one 3x4 increment.
+int icp_register_p2p(icpsymm_ctx* ctx, int max_iters, float thr, float* T_out, icpsymm_stats* stats) {
+    CloudSet& S = ctx->src;
+    CloudSet& Tg = ctx->tgt;
+    { int jr = icp_join_clouds(ctx, true); if (jr < 0) return jr; }
+    if (!S.valid || !Tg.valid) return icp_fail_msg(ctx, ICPSYMM_ERR_NOT_READY, "set_source / set_target first");
+    if (S.nseg != 1 || Tg.nseg != 1) return icp_fail_msg(ctx, ICPSYMM_ERR_INVALID, "RegisterP2P takes single pairs");
+    if (max_iters < 0) return icp_fail_msg(ctx, ICPSYMM_ERR_INVALID, "max_iters < 0");
+    const size_t n = S.h_counts[0];
+    if (n < 3 || Tg.h_counts[0] < 1) return icp_fail_msg(ctx, ICPSYMM_ERR_SIZE, "registrateNPoint needs >= 3 pairs (regist.h:9)");
+    int nblocks = (int)((n + kThreads - 1) / kThreads);
+    if (nblocks > 1024) nblocks = 1024;
+    const size_t pts_bytes = sizeof(double) * 3 * n;
+    const size_t need = 2 * pts_bytes + sizeof(double) * ((size_t)nblocks * kRow + 32);
+    cudaStream_t st = ctx->stream;
+    double Tt[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    icpsymm_stats last;
+    memset(&last, 0, sizeof last);
+    int it = 0, rc = ICPSYMM_OK;
+    float total_ms = 0.f;
+    for (;;) {
+        float Tf[16];
+        for (int i = 0; i < 16; i++) Tf[i] = (float)Tt[i];
+        rc = icp_run_single(ctx, Tf, nullptr, &last);            // search + diff on the device (K1 + K2)
+        if (rc < 0) return rc;
+        total_ms += last.loop_ms;
+        if (!(last.diff > (double)thr) || it >= max_iters) break;   // myicp.cpp:123
+        char* p = (char*)ctx->io_buf;                            // (icp_run_single does not use the scratch)
+        if ((rc = icp_reserve(ctx, &p, &ctx->io_bytes, need))) return rc;
+        ctx->io_buf = p;
+        double* d_src = (double*)p;
+        double* d_dst = d_src + 3 * n;
+        double* d_part = d_dst + 3 * n;
+        double* d_mean = d_part + (size_t)nblocks * kRow;
+        double* d_out = d_mean + 8;
+        T12f t12;
+        for (int i = 0; i < 12; i++) t12.m[i] = Tf[i];
+        p2p_pairs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(S.view(), Tg.view(), ctx->corr_pos, t12, d_src, d_dst);
+        kabsch_reduce_kernel<<<nblocks, kThreads, 0, st>>>(d_src, d_dst, n, nullptr, 0, d_part);
+        kabsch_means_kernel<<<1, 32, 0, st>>>(d_part, nblocks, n, d_mean);
+        kabsch_reduce_kernel<<<nblocks, kThreads, 0, st>>>(d_src, d_dst, n, d_mean, 1, d_part);
+        kabsch_solve_kernel<<<1, 32, 0, st>>>(d_part, nblocks, d_mean, d_out);
+        ICP_CUDA_CHECK(cudaGetLastError());
+        double o[12];
+        ICP_CUDA_CHECK(cudaMemcpyAsync(o, d_out, sizeof o, cudaMemcpyDeviceToHost, st));
+        ICP_CUDA_CHECK(cudaStreamSynchronize(st));
+        const double inc[16] = {o[0], o[1], o[2], o[9], o[3], o[4], o[5], o[10], o[6], o[7], o[8], o[11], 0, 0, 0, 1};
+        double out[16];
+        for (int r = 0; r < 4; r++)
+            for (int c = 0; c < 4; c++) {
+                double sacc = 0;
+                for (int k = 0; k < 4; k++) sacc += inc[4 * r + k] * Tt[4 * k + c];
+                out[4 * r + c] = sacc;
+            }
+        memcpy(Tt, out, sizeof out);                             // transform = incre * transform (myicp.cpp:138)
+        it++;
+    }
+    if (T_out) for (int i = 0; i < 16; i++) T_out[i] = (float)Tt[i];
+    if (stats) {
+        *stats = last;
+        stats->iters = it; stats->searches = it + 1; stats->converged = !(last.diff > (double)thr) ? 1 : 0;
+        stats->loop_ms = total_ms;
+    }
+    return ICPSYMM_OK;
+}
 
 int icp_kabsch(icpsymm_ctx* ctx, const double* src, const double* dst, size_t n, double R[9], double T[3]) {
     if (!src || !dst || !R || !T) return icp_fail_msg(ctx, ICPSYMM_ERR_INVALID, "null argument");

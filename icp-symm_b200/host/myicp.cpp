@@ -99,52 +99,16 @@ void MyICP::RegisterP2P() { RegisterP2P(max_iters, diff_threshold); }
 
 // The reference's RegisterP2P (myicp.cpp:43-59) only applies an identity guess.  This is the
 // point-to-point loop it stands for: exact correspondences on the device, closed-form fit of the
-// matched pairs (registrateNPoint, regist.h:8-72) on the device, repeat.
+// matched pairs (registrateNPoint, regist.h:8-72) on the device, repeat -- icpsymm_register_p2p: nothing but one diff
+// and one 3x4 increment per iteration crosses the bus.
 void MyICP::RegisterP2P(int iters, float threshold) {
     if (upload() < 0) { fprintf(stderr, "RegisterP2P: %s\n", LastError()); return; }
-    const size_t n = cloud_src->size();
-    std::vector<int32_t> idx(n);
-    std::vector<float> moved(3 * n);
-    std::vector<double> a(3 * n), b(3 * n);
-    double Tt[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
-    int it = 0;
-    double diff = 0;
-    for (;;) {
-        float Tf[16];
-        for (int i = 0; i < 16; i++) Tf[i] = (float)Tt[i];
-        status_ = icpsymm_find_correspondences(ctx_, Tf, idx.data(), nullptr);
-        if (status_ < 0) break;
-        status_ = icpsymm_eval_diff(ctx_, Tf, &diff);
-        if (status_ < 0) break;
-        if (verbose_) printf("iters# %d\ndiff: %g\n", it, diff);
-        if (!(diff > threshold) || it >= iters) break;
-        status_ = icpsymm_get_transformed_source(ctx_, Tf, moved.data(), 12);
-        if (status_ < 0) break;
-        size_t m = 0;
-        for (size_t i = 0; i < n; i++) {
-            if (idx[i] < 0) continue;
-            const PointT& q = cloud_tgt->points[(size_t)idx[i]];
-            a[3 * m] = moved[3 * i]; a[3 * m + 1] = moved[3 * i + 1]; a[3 * m + 2] = moved[3 * i + 2];
-            b[3 * m] = q.x; b[3 * m + 1] = q.y; b[3 * m + 2] = q.z;
-            m++;
-        }
-        double R[9], t[3];
-        status_ = icpsymm_register_npoint(ctx_, a.data(), b.data(), m, R, t);
-        if (status_ < 0) break;
-        double inc[16] = {R[0], R[1], R[2], t[0], R[3], R[4], R[5], t[1], R[6], R[7], R[8], t[2], 0, 0, 0, 1}, out[16];
-        for (int r = 0; r < 4; r++)
-            for (int c = 0; c < 4; c++) {
-                double s = 0;
-                for (int k = 0; k < 4; k++) s += inc[4 * r + k] * Tt[4 * k + c];
-                out[4 * r + c] = s;
-            }
-        memcpy(Tt, out, sizeof out);
-        it++;
-    }
+    icpsymm_stats st;
+    status_ = icpsymm_register_p2p(ctx_, iters, threshold, result_.transform.data(), &st);
     if (status_ < 0) { fprintf(stderr, "RegisterP2P: %s\n", LastError()); return; }
-    for (int i = 0; i < 16; i++) result_.transform[i] = (float)Tt[i];
-    result_.iterations = it; result_.diff = diff; result_.converged = !(diff > threshold);
-    result_.rmse = 0; result_.degenerate = false;
+    result_.iterations = st.iters; result_.diff = st.diff; result_.converged = st.converged != 0;
+    result_.rmse = st.rmse; result_.degenerate = false;
+    if (verbose_) printf("iters# %d\ndiff: %g\n", st.iters, st.diff);
     printResult("guess matrix:");                        // myicp.cpp:53
 }
 

@@ -82,6 +82,7 @@ def load():
         "icpsymm_get_trace": (C.c_int, [vp, sz, C.c_int, fp, dp]),
         "icpsymm_register_npoint": (C.c_int, [vp, dp, dp, sz, dp, dp]),
         "icpsymm_get_search_times": (C.c_int, [vp, fp, fp, C.c_int]),
+        "icpsymm_register_p2p": (C.c_int, [vp, C.c_int, C.c_float, fp, C.POINTER(Stats)]),
         "icpsymm_comm_unique_id": (C.c_int, [vp]),
         "icpsymm_comm_init": (C.c_int, [vp, vp, C.c_int, C.c_int]),
         "icpsymm_comm_destroy": (C.c_int, [vp]),
@@ -266,6 +267,13 @@ class Context:
         if self.n_pairs == 1:
             return T.reshape(4, 4), stats[0], rc
         return T.reshape(-1, 4, 4), stats, rc
+
+    def register_p2p(self, max_iters=10, diff_threshold=1.0):
+        """point-to-point ICP (MyICP::RegisterP2P): correspondences + closed-form fit, all on the device"""
+        T = np.empty(16, np.float32)
+        st = Stats()
+        rc = self._check(self.L.icpsymm_register_p2p(self.h, max_iters, diff_threshold, _fp(T), C.byref(st)))
+        return T.reshape(4, 4), st.as_dict(), rc
 
     def register_symm_async(self, max_iters=10, diff_threshold=1.0):
         """enqueue the loop and return; wait() hands out the result"""

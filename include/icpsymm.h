@@ -170,6 +170,11 @@ int icpsymm_get_search_times(icpsymm_ctx* ctx, float* search_ms, float* solve_ms
 int icpsymm_register_npoint(icpsymm_ctx* ctx, const double* src_xyz, const double* dst_xyz, size_t n,
                             double R[9], double T[3]);
 
+/* ---- point-to-point ICP (MyICP::RegisterP2P, myicp.h:18; a stub in the reference, myicp.cpp:43-59): the loop of
+ * myicp.cpp:121-142 with the closed-form fit of the matched pairs (registrateNPoint) as its step; single pairs, no normals
+ * needed; correspondences, pair gathering, fit and composition all run on the device ---- */
+int icpsymm_register_p2p(icpsymm_ctx* ctx, int max_iters, float diff_threshold, float T_out[16], icpsymm_stats* stats);
+
 /* ---- multi-GPU.  Pair batches need nothing: each rank registers its own pairs.
  * Query sharding: every rank holds the full clouds; rank r of n_ranks <= 8 searches its slice of the sorted
  * source and the 37-value normal equations are summed across ranks before the solve.  The sums have a

@@ -793,3 +793,28 @@ def test_async_registration_pipelines_two_contexts(cat, cat_out):
     finally:
         for c in pool:
             c.close()
+
+
+def test_register_p2p_matches_the_oracle_loop(ctx, cat, cat_out, gold):
+    """icpsymm_register_p2p (MyICP::RegisterP2P): exact correspondences + registrateNPoint per iteration, on the device,
+    against the same loop made of oracle pieces (kd-tree NN, regist.h restatement)"""
+    ctx.set_source(cat); ctx.set_target(cat_out)
+    T, st, _ = ctx.register_p2p(60, 0.5)
+    Tt, tree = np.eye(4), orc.KdTree(cat_out)
+    for it in range(61):
+        p = orc.transform_points(Tt.astype(np.float32), cat)
+        idx, d2 = tree.nn(p)
+        diff = np.sqrt(d2.astype(np.float64)).sum()
+        if not diff > 0.5 or it >= 60:
+            break
+        rc, R, t = orc.registrate_npoint(p.astype(np.float64), cat_out[idx].astype(np.float64))
+        inc = np.eye(4); inc[:3, :3] = R; inc[:3, 3] = t
+        Tt = inc @ Tt
+    assert st["iters"] == it and st["searches"] == it + 1
+    assert wl.rotation_angle(T, Tt) < 1e-5 and np.abs(T[:3, 3] - Tt[:3, 3]).max() < 1e-5 * wl.extent(cat)
+    assert st["diff"] == pytest.approx(diff, rel=1e-5)
+    di, dd = ctx.get_correspondences()
+    oi, od = tree.nn(orc.transform_points(T, cat))
+    assert np.array_equal(di, oi) and np.array_equal(dd, od)
+    with pytest.raises(icp.IcpError):
+        ctx.set_source(cat[:2]); ctx.register_p2p(5, 0.5)            # regist.h:9: fewer than 3 pairs
