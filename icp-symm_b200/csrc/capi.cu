@@ -99,7 +99,7 @@ void icpsymm_destroy(icpsymm_ctx* ctx) {
     cudaFree(ctx->d_state); cudaFree(ctx->d_lp); cudaFree(ctx->d_ctrl);
     cudaFree(ctx->corr_pos); cudaFree(ctx->partial); cudaFree(ctx->gsum); cudaFree(ctx->gparts); cudaFree(ctx->trace_T);
     cudaFree(ctx->trace_diff); cudaFree(ctx->io_buf); cudaFree(ctx->order_buf); cudaFree(ctx->order_temp);
-    cudaFree(ctx->margin2); cudaFree(ctx->ref_search); cudaFree(ctx->hist);
+    cudaFree(ctx->margin2); cudaFree(ctx->ref_search); cudaFree(ctx->hist); cudaFree(ctx->tile_seed);
     if (ctx->h_state) cudaFreeHost(ctx->h_state);
     if (ctx->done_ev) cudaEventDestroy(ctx->done_ev);
     if (ctx->ev_begin) cudaEventDestroy(ctx->ev_begin);
@@ -134,6 +134,7 @@ int icpsymm_set_option(icpsymm_ctx* ctx, int key, double value) {
         case ICPSYMM_OPT_GRID_BLOCKS: if (value < 0) return ICPSYMM_ERR_INVALID; ctx->opt_grid_blocks = (int)value; break;
         case ICPSYMM_OPT_TILE_ORDER: ctx->opt_tile_order = value != 0; break;
         case ICPSYMM_OPT_SKIP_WALK: ctx->opt_skip_walk = value != 0; break;
+        case ICPSYMM_OPT_PROBE: ctx->opt_probe = value != 0; break;
         case ICPSYMM_OPT_ASYNC_SETUP: {
             int jr = icp_join_clouds(ctx, true);   // never switch modes with work in flight
             ctx->opt_async_setup = value != 0;

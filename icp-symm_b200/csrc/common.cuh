@@ -112,7 +112,7 @@ struct SegState {
     int degenerate;
     int track;           // walks of the next search record margins (the last step was small, see solve_kernel)
     int have_margins;    // the search that ran last recorded margins
-    int pad;
+    int probe;           // the next search starts with one exact probe per 256-query tile (the last step was large)
     double radius;       // half diagonal of the target's bounding box
     double spacing;      // typical point spacing of the target taken as a surface: extent / sqrt(points)
 };
@@ -127,6 +127,7 @@ struct LoopParams {
     int warm_start;
     int trace;
     int skip_walk;       // 1 = skip the walk of a unit whose winners provably stand (margin test in K1)
+    int probe;           // 1 = searches after a long step start with one exact probe per tile
 };
 
 // ---- pinned fp32 arithmetic -------------------------------------------------------------

@@ -75,6 +75,12 @@ constexpr int kTilesPerTicket = ICP_TILES_PER_TICKET;
 #define ICP_TILES_PER_TICKET_SKIP 2
 #endif
 constexpr int kTilesPerTicketSkip = ICP_TILES_PER_TICKET_SKIP > ICP_TILES_PER_TICKET ? ICP_TILES_PER_TICKET_SKIP : ICP_TILES_PER_TICKET;
+#ifndef ICP_PROBE_BUDGET
+#define ICP_PROBE_BUDGET 24   // leaf scans a probe may spend (an ordinary far query needs about 40; 24, 48, 96 measured alike)
+#endif
+#ifndef ICP_PROBE_STEP_SPACINGS
+#define ICP_PROBE_STEP_SPACINGS 64.0   // probe the next search when a step moves some point by more than this many point spacings
+#endif
 #ifndef ICP_TRACK_STEP_SPACINGS
 #define ICP_TRACK_STEP_SPACINGS 4.0   // record margins once a step moves no point by more than this many point spacings
 #endif
@@ -98,6 +104,7 @@ struct NNParams {
     const uint32_t* order;    // ticket -> work item (null: identity)
     // walk skipping (see the skip test in K1): per query the margin of its last tracked walk and the search in which
     // that walk happened, per pair the fp32 transform of every search so far
+    uint32_t* tile_seed;      // [pair][tiles_max]: sorted target position of the neighbour of the tile's middle query (probe)
     float* margin2;
     uint8_t* ref_search;      // 0xff = the query has no margin (never walked with tracking in this registration)
     const float* hist;
@@ -135,6 +142,7 @@ struct InitArgs {
     float T[12];
     double origin[3];
     int has_T, has_origin;
+    int probe;   // the first search is probed
 };
 
 __global__ void set_lp_kernel(LoopParams* dst, LoopParams v) { *dst = v; }
@@ -159,6 +167,7 @@ __global__ void init_state_kernel(SegState* state, uint32_t nseg, InitArgs a, co
     st.origin[1] = a.has_origin ? (double)(float)a.origin[1] : (double)(0.5f * (lo.y + hi.y));
     st.origin[2] = a.has_origin ? (double)(float)a.origin[2] : (double)(0.5f * (lo.z + hi.z));
     st.min_ratio = 1.0;
+    st.probe = a.probe;
     const double ex = (double)hi.x - lo.x, ey = (double)hi.y - lo.y, ez = (double)hi.z - lo.z;
     st.radius = 0.5 * sqrt(ex * ex + ey * ey + ez * ez);
     st.spacing = 2.0 * st.radius / sqrt((double)(tgt_counts[s] ? tgt_counts[s] : 1u));
@@ -235,6 +244,40 @@ __global__ void __launch_bounds__(256) tile_cost_kernel(CloudView src, CloudView
 // ------------------------------------------------------------------------------------------------
 // K1: search + accumulate
 // ------------------------------------------------------------------------------------------------
+// PROBE.  While the clouds are far apart a search starts blind: the previous correspondences are useless as bounds
+// (the last step moved every point a long way) and a packet pays for that until its first good candidates turn up
+// (measured: a far search seeded with a neighbouring query's true neighbour is 20-25 % cheaper).  So before such a
+// search one warp per 256-query tile finds the exact neighbour of the tile's MIDDLE query -- the ordinary walk with a
+// single live lane, about 1/3 of a packet walk for 1/8 of the units -- and K1 offers that point to all 256 queries of
+// the tile first.  A seed is only ever a candidate: the result stays exact.  K2 turns the probe off once a step is small.
+__global__ void __launch_bounds__(kNNThreads, kNNBlocksPerSM) probe_kernel(const __grid_constant__ NNParams P) {
+    const uint32_t w = (blockIdx.x * (uint32_t)kNNThreads + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
+    if (w >= P.total_work) return;
+    const uint32_t seg = w / P.work_per_seg;
+    const SegState* st = P.state + seg;
+    if (st->done || !st->probe) return;
+    const uint32_t ns = P.src.counts[seg], nt = P.tgt.counts[seg];
+    const uint32_t tiles = icp_tiles(ns);
+    const uint32_t tile = icp_part_tile_lo(tiles, P.part0) + (w - seg * P.work_per_seg);
+    if (tile >= icp_part_tile_lo(tiles, P.part0 + P.nparts) || nt == 0) return;
+    uint32_t i = tile * ICP_TILE + ICP_TILE / 2;
+    if (i >= ns) i = ns - 1;
+    const float4 s = ldg4(P.src.pts + (size_t)seg * P.src.shape.pitch + i);
+    const float3 p = apply_rn(st->Tf, s.x, s.y, s.z);
+    const float4* tpts = P.tgt.pts + (size_t)seg * P.tgt.shape.pitch;
+    Best b;
+    best_init(b);
+    const uint32_t prev = P.corr_pos[(size_t)seg * P.src.shape.pitch + i];
+    if (prev < nt) best_offer(b, ldg4(tpts + prev), p.x, p.y, p.z);
+    const unsigned long long key = nn_walk_budget(&P.tgt.shape, P.tgt.nodes + (size_t)seg * P.tgt.shape.nodes_per_seg, tpts, p.x,
+                                                  p.y, p.z, lane == 0, b.key, ICP_PROBE_BUDGET);
+    if (lane == 0) {
+        const uint32_t id = (uint32_t)key;
+        P.tile_seed[(size_t)seg * P.tiles_max + tile] =
+            id != (uint32_t)ICP_INVALID_ID ? __ldg(P.tgt.pos_of_orig + (size_t)seg * P.tgt.shape.pitch + id) : 0xffffffffu;
+    }
+}
+
 // Persistent blocks (4 per SM) draw 256-query tiles from a global ticket counter; ticket k is tile
 // order[k] (most expensive first, see tile_cost_kernel) or simply tile k.  The 8 warps of a block always
 // work on the SAME tile: they share its node records and leaf lines in L1, which is worth more than
@@ -254,6 +297,7 @@ __global__ void __launch_bounds__(kNNThreads, kNNBlocksPerSM) nn_accum_kernel(co
     __shared__ int sDone;
     __shared__ uint32_t sSearch;      // index of the running search of the block's current pair
     __shared__ int sTrack;            // walks of this search record margins (K2 expects the next step to be small)
+    __shared__ int sProbe;            // the probe kernel has left one seed per tile
     __shared__ uint32_t sWork[2];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const LoopParams lp = *P.lp;
@@ -276,7 +320,7 @@ __global__ void __launch_bounds__(kNNThreads, kNNBlocksPerSM) nn_accum_kernel(co
         const uint32_t seg = we / tickets_per_seg;
         if (seg != cur_seg) {   // block-uniform: (re)load the pair's transform and origin
             const SegState* st = P.state + seg;
-            if (tid == 0) { sDone = st->done; sSearch = (uint32_t)st->searches; sTrack = st->track; }
+            if (tid == 0) { sDone = st->done; sSearch = (uint32_t)st->searches; sTrack = st->track; sProbe = st->probe; }
             if (tid < 12) sT[tid] = st->Tf[tid];
             if (tid < 3) sO[tid] = (float)st->origin[tid];
             __syncthreads();
@@ -328,6 +372,10 @@ __global__ void __launch_bounds__(kNNThreads, kNNBlocksPerSM) nn_accum_kernel(co
             } else {
                 uint32_t prev = lp.warm_start ? corr[i] : 0xffffffffu;
                 if (prev < nt) best_offer(b, ldg4(tpts + prev), p.x, p.y, p.z);
+                if (sProbe) {   // the neighbour of the tile's middle query (probe_kernel): a good first bound for all 256
+                    const uint32_t sp = P.tile_seed[(size_t)seg * P.tiles_max + tile];
+                    if (sp < nt) best_offer(b, ldg4(tpts + sp), p.x, p.y, p.z);
+                }
                 const uint32_t ref = may_skip ? (uint32_t)P.ref_search[(size_t)seg * P.src.shape.pitch + i] : 0xffu;
                 if (ref < P.hist_stride && ref != 0xffu && prev < nt) {
                     const float3 xr = apply_rn(P.hist + ((size_t)seg * P.hist_stride + ref) * 12, s.x, s.y, s.z);
@@ -812,6 +860,7 @@ __global__ void __launch_bounds__(kSolveThreads) solve_kernel(const __grid_const
         const double step = sqrt(mx * mx + my * my + mz * mz) + 2.0 * atan(an) * st->radius;
         st->have_margins = st->track;   // what the search that has just run recorded
         st->track = step < ICP_TRACK_STEP_SPACINGS * st->spacing ? 1 : 0;
+        st->probe = (lp.probe && step >= ICP_PROBE_STEP_SPACINGS * st->spacing) ? 1 : 0;   // after a long step the old pairs are no bounds
     }
     st->iter = st->iter + 1;
     st->pairs = (unsigned long long)(sS[36] + 0.5);
@@ -899,6 +948,7 @@ static void launch_iteration(icpsymm_ctx* ctx, const NNParams& np, SolveParams s
                              cudaEvent_t* ev /*4 events or null*/) {
     cudaStream_t st = ctx->stream;
     if (ev) cudaEventRecord(ev[0], st);
+    if (np.tile_seed) probe_kernel<<<(np.total_work * 32u + kNNThreads - 1u) / kNNThreads, kNNThreads, 0, st>>>(np);
     nn_accum_kernel<<<np.grid, kNNThreads, 0, st>>>(np);
     if (ev) { cudaEventRecord(ev[1], st); cudaEventRecord(ev[2], st); }
     if (!use_comm) {
@@ -960,6 +1010,7 @@ int icp_loop_enqueue(icpsymm_ctx* ctx, int max_iters, float thr, const float* T_
     if ((rc = icp_reserve(ctx, &ctx->corr_pos, &ctx->corr_cap, (size_t)nseg * S.shape.pitch))) return rc;
     const uint32_t hist_stride = (uint32_t)(single_search ? 1 : max_iters + 2);
     if ((rc = icp_reserve(ctx, &ctx->margin2, &ctx->margin_cap, (size_t)nseg * S.shape.pitch))) return rc;
+    if ((rc = icp_reserve(ctx, &ctx->tile_seed, &ctx->tile_seed_cap, (size_t)nseg * bps))) return rc;
     if ((rc = icp_reserve(ctx, &ctx->ref_search, &ctx->ref_cap, (size_t)nseg * S.shape.pitch))) return rc;
     if ((rc = icp_reserve(ctx, &ctx->hist, &ctx->hist_cap, (size_t)nseg * hist_stride * 12))) return rc;
     if (!ctx->d_lp) ICP_CUDA_CHECK(cudaMalloc((void**)&ctx->d_lp, sizeof(LoopParams)));
@@ -987,6 +1038,7 @@ int icp_loop_enqueue(icpsymm_ctx* ctx, int max_iters, float thr, const float* T_
     lp.warm_start = ctx->opt_warm_start;
     lp.trace = ctx->opt_trace;
     lp.skip_walk = ctx->opt_skip_walk;
+    lp.probe = (ctx->opt_probe && !ctx->opt_identity) ? 1 : 0;
     set_lp_kernel<<<1, 1, 0, st>>>(ctx->d_lp, lp);
 
     InitArgs ia;
@@ -995,6 +1047,7 @@ int icp_loop_enqueue(icpsymm_ctx* ctx, int max_iters, float thr, const float* T_
         ia.has_T = 1;
         for (int i = 0; i < 12; i++) ia.T[i] = T_init[i];
     }
+    ia.probe = (ctx->opt_probe && !ctx->opt_identity) ? 1 : 0;
     if (origin) {
         ia.has_origin = 1;
         for (int i = 0; i < 3; i++) ia.origin[i] = origin[i];
@@ -1036,6 +1089,7 @@ int icp_loop_enqueue(icpsymm_ctx* ctx, int max_iters, float thr, const float* T_
     sp.trace_diff = ctx->opt_trace ? ctx->trace_diff : nullptr;
     sp.trace_stride = ctx->trace_stride; sp.mode = single_search ? 3 : 0;
     np.ctrl = (LoopCtrl*)ctx->d_ctrl; np.order = nullptr;
+    np.tile_seed = (ctx->opt_probe && !ctx->opt_identity) ? ctx->tile_seed : nullptr;
     np.margin2 = ctx->margin2; np.ref_search = ctx->ref_search; np.hist = ctx->hist; np.hist_stride = hist_stride;
     // most-expensive-first order of the first search (single pairs that fill the machine more than twice)
     if (nseg == 1 && !ctx->opt_identity && ctx->opt_tile_order && np.total_work >= 2u * np.grid && T.shape.n_levels >= 4) {
@@ -1096,7 +1150,7 @@ int icp_loop_enqueue(icpsymm_ctx* ctx, int max_iters, float thr, const float* T_
         key.generation = ctx->generation;
         key.shard_rank = ctx->shard_rank; key.shard_world = ctx->shard_world; key.trace = ctx->opt_trace;
         key.trace_stride = ctx->opt_trace ? ctx->trace_stride : 0;
-        key.mode = ctx->opt_use_graph + 16 * ctx->peer_world + (np.order ? 1024 : 0);
+        key.mode = ctx->opt_use_graph + 16 * ctx->peer_world + (np.order ? 1024 : 0) + (np.tile_seed ? 2048 : 0);
         if (!ctx->graph_exec || !(ctx->graph_key == key)) {
             if (ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }
             cudaGraph_t g = nullptr;

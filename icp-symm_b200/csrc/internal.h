@@ -85,6 +85,7 @@ struct icpsymm_ctx {
     LoopParams* d_lp = nullptr;
     void* d_ctrl = nullptr;       // LoopCtrl: ticket + done counter of the device-side loop
     uint32_t* corr_pos = nullptr; size_t corr_cap = 0;
+    uint32_t* tile_seed = nullptr; size_t tile_seed_cap = 0;   // per tile: neighbour of its middle query (probe kernel)
     float* margin2 = nullptr;     size_t margin_cap = 0;   // per query: margin of its last walk (K1 skip test)
     uint8_t* ref_search = nullptr; size_t ref_cap = 0;     // per query: search of its last tracked walk (0xff: none)
     float* hist = nullptr;        size_t hist_cap = 0;     // per pair: fp32 transform of every search
@@ -113,6 +114,7 @@ struct icpsymm_ctx {
     int opt_async_setup = 0;
     int opt_tile_order = 1;
     int opt_skip_walk = 1;
+    int opt_probe = 1;
     double opt_peer_timeout_ms = 10000.0;
 
     // graph cache

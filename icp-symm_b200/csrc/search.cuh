@@ -265,6 +265,7 @@ __device__ __forceinline__ void wide_traverse_group(const TreeShape& sh, const W
     uint32_t cur = warp_node_test(rec, qx, qy, qz, v.bound_bits(), active, pb, max_bound, far_mode, pref, v);
     unsigned long long saved = 0ull;   // byte l-1: pending mask of the open ancestor at level l
     for (;;) {
+        if (V::kBudget && v.exhausted()) break;
         if (cur == 0u) {
             if (l == top) break;
             ++l; i >>= ICP_LOG_FAN;
@@ -322,9 +323,12 @@ __device__ __forceinline__ void wide_traverse_warp(const TreeShape& sh, const Wi
 // pinned fp32 arithmetic (a box bound never exceeds the fp32 distance of a member point).  K1 stores it and uses it
 // in later searches: while the query has moved by less than the gap between the winner's distance and the margin,
 // the winner cannot have changed and the walk is skipped (icp_loop.cu).
-template <bool TRACK>
+template <bool TRACK, bool BUDGET = false>
 struct NNVisitor {
     static constexpr bool kTrackMargin = TRACK;
+    static constexpr bool kBudget = BUDGET;   // the walk may stop early (probe: any real point is a useful seed)
+    int budget = 0;                           // leaf scans left
+    __device__ __forceinline__ bool exhausted() const { return BUDGET && budget <= 0; }
     Best& b;
     const float4* __restrict__ pts;
     float qx, qy, qz;
@@ -334,7 +338,10 @@ struct NNVisitor {
     __device__ __forceinline__ void set_active(bool) {}
     __device__ __forceinline__ void prune(uint32_t lower_bound_bits) { if (TRACK) m2 = min(m2, lower_bound_bits); }
     // warp-uniform call; returns whether some active lane's bound changed
-    __device__ __forceinline__ bool leaf(uint32_t g, bool active) { return scan_leaf_lazy<TRACK>(pts, g, nq, active, b, m2); }
+    __device__ __forceinline__ bool leaf(uint32_t g, bool active) {
+        if (BUDGET) budget--;
+        return scan_leaf_lazy<TRACK>(pts, g, nq, active, b, m2);
+    }
 };
 
 // full exact 1-NN search of all lanes of a warp; each `b` may already hold a candidate (warm start).
@@ -362,9 +369,20 @@ template <bool TRACK>
 __device__ __forceinline__ uint32_t nn_traverse_warp(const TreeShape& sh, const WideNode* __restrict__ seg_nodes,
                                                      const float4* __restrict__ seg_pts, float qx, float qy, float qz,
                                                      bool active, uint32_t split_mask, Best& b) {
-    NNVisitor<TRACK> v{b, seg_pts, qx, qy, qz, make_neg_query(qx, qy, qz), TRACK ? ICP_INF_BITS : 0u};
+    NNVisitor<TRACK> v{0, b, seg_pts, qx, qy, qz, make_neg_query(qx, qy, qz), TRACK ? ICP_INF_BITS : 0u};
     wide_traverse_warp(sh, seg_nodes, qx, qy, qz, active, split_mask, v);
     return v.m2;
+}
+
+// the probe's walk: exact unless it runs out of its budget of leaf scans, in which case it returns the best point
+// met so far (a query next to the medial axis of the target would otherwise walk for a millisecond on its own)
+static __device__ __noinline__ unsigned long long nn_walk_budget(const TreeShape* sh, const WideNode* __restrict__ seg_nodes,
+                                                          const float4* __restrict__ seg_pts, float qx, float qy, float qz,
+                                                          bool active, unsigned long long key, int budget) {
+    Best b; b.key = key;
+    NNVisitor<false, true> v{budget, b, seg_pts, qx, qy, qz, make_neg_query(qx, qy, qz), 0u};
+    wide_traverse_warp(*sh, seg_nodes, qx, qy, qz, active, 0u, v);
+    return b.key;
 }
 
 // ---- k nearest ------------------------------------------------------------------------------
@@ -490,6 +508,8 @@ __device__ __forceinline__ void knn_offer_leaf(KList<KMAX, EXACT>& L, const floa
 template <int KMAX, bool EXACT>
 struct KnnVisitor {
     static constexpr bool kTrackMargin = false;
+    static constexpr bool kBudget = false;
+    __device__ __forceinline__ bool exhausted() const { return false; }
     __device__ __forceinline__ void prune(uint32_t) {}
     KList<KMAX, EXACT>& L;
     const float4* __restrict__ pts;

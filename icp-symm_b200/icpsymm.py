@@ -19,7 +19,7 @@ OK, WARN_DEGENERATE = 0, 1
 ERR_INVALID, ERR_CUDA, ERR_NOT_READY, ERR_SIZE, ERR_NONFINITE, ERR_COMM = -1, -2, -3, -4, -5, -6
 OPT_REL_DIFF_TOL, OPT_IDENTITY_PAIRS, OPT_MAX_PAIR_DIST, OPT_USE_GRAPH = 1, 2, 3, 4
 OPT_KERNEL_TIMING, OPT_WARM_START, OPT_TRACE, OPT_GRID_BLOCKS, OPT_ASYNC_SETUP = 5, 6, 7, 8, 9
-OPT_MIN_NORMAL_DOT, OPT_PEER_TIMEOUT_MS, OPT_TILE_ORDER, OPT_SKIP_WALK = 10, 11, 12, 13
+OPT_MIN_NORMAL_DOT, OPT_PEER_TIMEOUT_MS, OPT_TILE_ORDER, OPT_SKIP_WALK, OPT_PROBE = 10, 11, 12, 13, 14
 
 
 class Stats(C.Structure):

@@ -83,6 +83,9 @@ enum {
                                        last walk (each query moved by less than the gap between its neighbour and everything
                                        else) keeps them without walking the index; 0 = always walk.
                                        Results are identical either way */
+    ICPSYMM_OPT_PROBE = 14,         /* 1 (default) = a search that follows a long step (and the first one) begins with one exact
+                                       single-query search per 256-query tile whose result seeds the whole tile; 0 = off.
+                                       Seeds are candidates only: results are identical */
     ICPSYMM_OPT_PEER_TIMEOUT_MS = 11, /* NVLink peer exchange: how long a rank waits for its peers' sums (default 10000 ms)
                                         before the call fails with ICPSYMM_ERR_COMM */
     ICPSYMM_OPT_ASYNC_SETUP = 9     /* 1 = set_source / set_target / estimate_normals return without waiting: each cloud is

@@ -27,6 +27,8 @@ def child(lib, n):
         L = ctx.L
         stream = torch.cuda.ExternalStream(ctx.stream)
         ctx.set_option(icp.OPT_REL_DIFF_TOL, 1e-5)
+        if os.environ.get("PROBE"):
+            ctx.set_option(icp.OPT_PROBE, int(os.environ["PROBE"]))
         if os.environ.get("TILE_ORDER"):
             ctx.set_option(icp.OPT_TILE_ORDER, int(os.environ["TILE_ORDER"]))
         import time
