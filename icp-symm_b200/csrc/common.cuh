@@ -33,20 +33,7 @@
 #define ICP_INVALID_ID 0x7fffffff
 #define ICP_MAX_PEERS 8                  // one NVSwitch domain
 
-// ---- canonical order of the normal-equation sums -------------------------------------------------
-// The queries of a pair are cut into 256-point tiles and the tiles into ICP_NPARTS contiguous parts; part
-// o owns tiles [T*o/8, T*(o+1)/8), T = ceil(n/256).  K1 leaves one fp64 row per TILE (whichever block drew
-// the tile), K2 adds the rows of a part in a fixed order and then the 8 part sums in part order.  Every
-// step depends on the pair's own point count only -- not on the grid, the batch the pair sits in, the
-// scheduling of the tiles or the number of GPUs: a query shard is a run of whole parts (rank r of W owns
-// parts [8r/W, 8(r+1)/W)), so a pair registered on 1, 2, 4 or 8 GPUs, alone or inside a batch, gives
-// bit-identical sums, transforms and correspondences.
-#define ICP_NPARTS 8
-#define ICP_TILE 256                     // queries per tile = threads of a K1 block
-__host__ __device__ __forceinline__ uint32_t icp_tiles(uint32_t n) { return (n + ICP_TILE - 1u) / ICP_TILE; }
-__host__ __device__ __forceinline__ uint32_t icp_part_tile_lo(uint32_t tiles, uint32_t part) {
-    return (uint32_t)(((unsigned long long)tiles * part) / ICP_NPARTS);
-}
+#include "parts.h"   // the canonical partition of a pair's queries into tiles and parts (plain C++, also compiled by the host self-test)
 
 // exchange buffer of the NVLink peer mode (one per rank, mapped by every peer): the owner of part o
 // stores the part's sums of exchange `seq` into sums[seq & 1][o] of EVERY rank's buffer and then

@@ -66,7 +66,10 @@ extern "C" __attribute__((visibility("default"))) int icpsymm_debug_tile_times(u
 namespace {
 
 constexpr int kNNThreads = ICP_TILE;   // one block = one 256-query tile at a time
-constexpr int kNNBlocksPerSM = 1024 / kNNThreads;   // 64 registers per thread: 1024 threads per SM
+#ifndef ICP_K1_BLOCKS
+#define ICP_K1_BLOCKS (1024 / ICP_TILE)   // 64 registers per thread: 1024 threads per SM (5 blocks = 51 registers: measured)
+#endif
+constexpr int kNNBlocksPerSM = ICP_K1_BLOCKS;
 #ifndef ICP_TILES_PER_TICKET
 #define ICP_TILES_PER_TICKET 1
 #endif
@@ -209,9 +212,9 @@ __global__ void __launch_bounds__(256) tile_cost_kernel(CloudView src, CloudView
     for (uint32_t k = 0; k < tiles_per_warp; k++) {
         const uint32_t wid = warp_global * tiles_per_warp + k;
         if (wid >= work) return;
-        const uint32_t tile = icp_part_tile_lo(tiles, part0) + wid;
+        const uint32_t tile = icp_shard_tile(tiles, part0, nparts, wid);
         uint32_t cost = 0u;
-        if (tile < icp_part_tile_lo(tiles, part0 + nparts) && tgt.counts[0] > 0) {
+        if (tile < tiles && tgt.counts[0] > 0) {
             uint32_t i = tile * ICP_TILE + ICP_TILE / 2;
             if (i >= ns) i = ns - 1;
             const float4 sp = ldg4(src.pts + i);
@@ -258,8 +261,8 @@ __global__ void __launch_bounds__(kNNThreads, kNNBlocksPerSM) probe_kernel(const
     if (st->done || !st->probe) return;
     const uint32_t ns = P.src.counts[seg], nt = P.tgt.counts[seg];
     const uint32_t tiles = icp_tiles(ns);
-    const uint32_t tile = icp_part_tile_lo(tiles, P.part0) + (w - seg * P.work_per_seg);
-    if (tile >= icp_part_tile_lo(tiles, P.part0 + P.nparts) || nt == 0) return;
+    const uint32_t tile = icp_shard_tile(tiles, P.part0, P.nparts, w - seg * P.work_per_seg);
+    if (tile >= tiles || nt == 0) return;
     uint32_t i = tile * ICP_TILE + ICP_TILE / 2;
     if (i >= ns) i = ns - 1;
     const float4 s = ldg4(P.src.pts + (size_t)seg * P.src.shape.pitch + i);
@@ -328,17 +331,16 @@ __global__ void __launch_bounds__(kNNThreads, kNNBlocksPerSM) nn_accum_kernel(co
         }
         const uint32_t ns = P.src.counts[seg], nt = P.tgt.counts[seg];
         const uint32_t tiles = icp_tiles(ns);
-        const uint32_t tile0 = icp_part_tile_lo(tiles, P.part0) + (we - seg * tickets_per_seg) * tpt;
-        const uint32_t tile_end = icp_part_tile_lo(tiles, P.part0 + P.nparts);
+        const uint32_t item0 = (we - seg * tickets_per_seg) * tpt;   // work items of this ticket: item0 .. item0 + tpt - 1
 #ifdef ICP_TILE_TIMES
         unsigned long long tt0;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt0));
 #endif
 #pragma unroll 1
         for (uint32_t sub = 0; sub < tpt; sub++) {
-        const uint32_t tile = tile0 + sub;
+        const uint32_t tile = icp_shard_tile(tiles, P.part0, P.nparts, item0 + sub);
         // block-uniform; a finished pair has nothing to do and a smaller pair of a batch has fewer tiles
-        const bool valid = !sDone && tile < tile_end;
+        const bool valid = !sDone && item0 + sub < P.work_per_seg && tile < tiles;
         float (*acc)[ICP_PART_STRIDE] = wacc[it & 1u][sub];
         if (valid) {
         const float4* __restrict__ spts = P.src.pts + (size_t)seg * P.src.shape.pitch;
@@ -476,8 +478,9 @@ __global__ void __launch_bounds__(kNNThreads, kNNBlocksPerSM) nn_accum_kernel(co
         if (tid == 0) sWork[it & 1u] = wnext;
         __syncthreads();
         if (!sDone && tid < (int)(tpt * ICP_PART_STRIDE)) {
-            const uint32_t sub = tid / ICP_PART_STRIDE, vi = tid - sub * ICP_PART_STRIDE, tile = tile0 + sub;
-            if (vi < ICP_NSUMS && tile < tile_end) {
+            const uint32_t sub = tid / ICP_PART_STRIDE, vi = tid - sub * ICP_PART_STRIDE;
+            const uint32_t tile = icp_shard_tile(tiles, P.part0, P.nparts, item0 + sub);
+            if (vi < ICP_NSUMS && item0 + sub < P.work_per_seg && tile < tiles) {
                 double s = 0.0;
 #pragma unroll
                 for (int ww = 0; ww < kNNWarps; ww++) s += (double)wacc[it & 1u][sub][ww][vi];
@@ -485,10 +488,10 @@ __global__ void __launch_bounds__(kNNThreads, kNNBlocksPerSM) nn_accum_kernel(co
             }
         }
 #ifdef ICP_TILE_TIMES
-        if (tid == 0 && tile0 < 65536u) {
+        if (tid == 0 && item0 < 65536u) {
             unsigned long long tt1;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt1));
-            icp_tile_times[2 * tile0] = tt0; icp_tile_times[2 * tile0 + 1] = tt1;
+            icp_tile_times[2 * item0] = tt0; icp_tile_times[2 * item0 + 1] = tt1;
         }
 #endif
         w = sWork[it & 1u];
@@ -710,14 +713,17 @@ __global__ void __launch_bounds__(kSolveThreads) solve_kernel(const __grid_const
                 // chain c adds the part's tile rows c, c + 27, c + 54, ... in that order; ICP_K2_BATCH loads are
                 // issued back to back so the (L2-latency) loads overlap instead of serialising with the adds
                 double s = 0.0;
-                const uint32_t t_lo = icp_part_tile_lo(tiles, P.part0 + ol);
-                const uint32_t own_blocks = icp_part_tile_lo(tiles, P.part0 + ol + 1u) - t_lo;   // rows of this part
-                const double* row = P.partial + ((size_t)seg * P.tiles_max + t_lo) * ICP_PART_STRIDE + v;
+                const uint32_t part = P.part0 + ol;
+                const uint32_t own_blocks = icp_part_tiles(tiles, part);   // rows of this part: its tiles in curve order
+                const uint32_t C = icp_part_chunk(tiles), lc = 31u - (uint32_t)__clz((int)C);   // C is a power of two
+                const double* row = P.partial + (size_t)seg * P.tiles_max * ICP_PART_STRIDE + v;
                 for (uint32_t b = chain; b < own_blocks; b += ICP_K2_BATCH * kSolveParts) {
                     double x[ICP_K2_BATCH];   // rows past the end count as 0.0, which leaves the sum unchanged
 #pragma unroll
                     for (int u = 0; u < ICP_K2_BATCH; u++)
-                        x[u] = (b + u * kSolveParts < own_blocks) ? row[(size_t)(b + u * kSolveParts) * ICP_PART_STRIDE] : 0.0;
+                        x[u] = (b + u * kSolveParts < own_blocks)
+                                   ? row[(size_t)(((((b + u * kSolveParts) >> lc) * ICP_NPARTS + part) << lc) +
+                                                  ((b + u * kSolveParts) & (C - 1u))) * ICP_PART_STRIDE] : 0.0;   // = icp_part_tile
 #pragma unroll
                     for (int u = 0; u < ICP_K2_BATCH; u++) s += x[u];
                 }
@@ -1058,7 +1064,7 @@ int icp_loop_enqueue(icpsymm_ctx* ctx, int max_iters, float thr, const float* T_
     }
     uint32_t k1_grid;
     {
-        const uint32_t wps = icp_part_tile_lo(bps, part0 + nparts) - icp_part_tile_lo(bps, part0) + 1u;
+        const uint32_t wps = icp_shard_work(bps, nparts);
         const uint32_t resident = (uint32_t)ctx->sm_count * (uint32_t)kNNBlocksPerSM;
         k1_grid = nseg * wps < resident ? nseg * wps : resident;
     }
@@ -1075,7 +1081,7 @@ int icp_loop_enqueue(icpsymm_ctx* ctx, int max_iters, float thr, const float* T_
     np.src = S.view(); np.tgt = T.view();
     np.state = ctx->d_state; np.lp = ctx->d_lp; np.corr_pos = ctx->corr_pos; np.partial = ctx->partial;
     np.tiles_max = bps; np.part0 = part0; np.nparts = nparts;
-    np.work_per_seg = icp_part_tile_lo(bps, part0 + nparts) - icp_part_tile_lo(bps, part0) + 1u;   // +1: floor of a smaller pair
+    np.work_per_seg = icp_shard_work(bps, nparts);
     np.total_work = nseg * np.work_per_seg;
     {
         const uint32_t resident = (uint32_t)ctx->sm_count * (uint32_t)kNNBlocksPerSM;   // persistent blocks
@@ -1255,9 +1261,13 @@ int icp_loop_finish(icpsymm_ctx* ctx, float* T_out, icpsymm_stats* stats) {
             uint32_t nq = S.h_counts[s];
             if (ctx->shard_world > 1) {
                 const uint32_t tiles = icp_tiles(nq);
-                uint32_t lo = icp_part_tile_lo(tiles, part0) * ICP_TILE, hi = icp_part_tile_lo(tiles, part0 + nparts) * ICP_TILE;
-                if (hi > nq) hi = nq;
-                nq = (use_comm || (ctx->peer_world > 1 && !single_search)) ? nq : hi - lo;   // global sums: all source points
+                uint32_t mine = 0;   // queries of this rank's parts
+                for (uint32_t o = part0; o < part0 + nparts; o++)
+                    for (uint32_t j = 0, n_o = icp_part_tiles(tiles, o); j < n_o; j++) {
+                        const uint32_t first = icp_part_tile(tiles, o, j) * ICP_TILE;
+                        mine += nq - first < ICP_TILE ? nq - first : ICP_TILE;
+                    }
+                nq = (use_comm || (ctx->peer_world > 1 && !single_search)) ? nq : mine;   // global sums: all source points
             }
             o.rmse = nq ? sqrt(hs.sumd2 / (double)nq) : 0.0;
             o.min_pivot_ratio = hs.min_ratio; o.pairs = hs.pairs;

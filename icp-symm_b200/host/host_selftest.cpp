@@ -2,8 +2,10 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <vector>
 
 #include "pcd_io.h"
+#include "../csrc/parts.h"
 
 using namespace icpsymm;
 
@@ -87,6 +89,43 @@ int main(int argc, char** argv) {
         fclose(f);
         PointCloud<PointXYZ> t;
         CHECK(loadXYZText(path, t) == 0 && t.points.size() == 2 && t.points[1].y == -3.03882f);
+    }
+    // the canonical partition (csrc/parts.h): for every tile count the 8 parts are a partition of the tiles, a part's
+    // j-th tile enumerates it in increasing order, a run of parts enumerates exactly its tiles in curve order, the work
+    // of a run is monotone in the tile count, and the parts are balanced to within one chunk
+    {
+        uint32_t prev_work[9] = {0};
+        for (uint32_t T = 1; T <= 6000; T += (T < 700 ? 1 : 37)) {
+            std::vector<int> owner(T, -1);
+            uint32_t total = 0, nmin = ~0u, nmax = 0;
+            for (uint32_t o = 0; o < ICP_NPARTS; o++) {
+                const uint32_t n_o = icp_part_tiles(T, o);
+                total += n_o; nmin = n_o < nmin ? n_o : nmin; nmax = n_o > nmax ? n_o : nmax;
+                uint32_t last = 0;
+                for (uint32_t j = 0; j < n_o; j++) {
+                    const uint32_t t = icp_part_tile(T, o, j);
+                    CHECK(t < T && owner[t] == -1 && (j == 0 || t > last));
+                    owner[t] = (int)o; last = t;
+                }
+            }
+            CHECK(total == T && nmax - nmin <= icp_part_chunk(T));
+            for (uint32_t W = 1; W <= 8; W++)
+                for (uint32_t r = 0; r < W; r++) {
+                    const uint32_t p0 = ICP_NPARTS * r / W, np = ICP_NPARTS * (r + 1) / W - p0;
+                    const uint32_t work = icp_shard_work(T, np);
+                    uint32_t seen = 0, last = 0;
+                    for (uint32_t w = 0; w < work; w++) {
+                        const uint32_t t = icp_shard_tile(T, p0, np, w);
+                        if (t >= T) continue;
+                        CHECK(owner[t] >= (int)p0 && owner[t] < (int)(p0 + np) && (seen == 0 || t > last));
+                        seen++; last = t;
+                    }
+                    uint32_t want = 0;
+                    for (uint32_t o = p0; o < p0 + np; o++) want += icp_part_tiles(T, o);
+                    CHECK(seen == want);
+                }
+            for (uint32_t np = 1; np <= 8; np++) { CHECK(icp_shard_work(T, np) >= prev_work[np]); prev_work[np] = icp_shard_work(T, np); }
+        }
     }
     printf("host selftest ok\n");
     return 0;
