@@ -236,6 +236,20 @@ def shard_sub(args, torch, dist, icp, rank, world, local_rank):
            "single_gpu_ms": single["ms"], "single_gpu_value": float(n) * single["iters"] / (single["ms"] * 1e-3),
            "rot_err_rad": wl.rotation_angle(T, Ttrue), "trans_err_over_extent": float(np.abs(T[:3, 3] - Ttrue[:3, 3]).max() / wl.extent(tgt)),
            "host_generation_s": gen_s}
+    # the DRAM-bound configuration (working set 1.2 GB >> 126 MB L2): algorithmic bytes against the measured peak, beside
+    # the dram bytes of the committed ncu capture of this very workload (profiles/r02_nn_accum_16m.json)
+    peak, peak_kind = measured_peak_gbs()
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_nn_accum_16m.json")) as f:
+            prof16 = json.load(f)
+    except Exception:
+        prof16 = {}
+    alg = BYTES_PER_CORR_FUSED * float(n) * single["searches"]
+    out["roofline"] = {"bound": "hbm", "kernel": "nn_accum_kernel, all searches of the unsharded 16M registration (incl. reduce+solve launches)",
+                       "achieved": alg / (single["ms"] * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                       "frac": alg / (single["ms"] * 1e-3) / 1e9 / peak, "peak_kind": f"of {peak_kind}",
+                       "traffic": prof16.get("dram_bytes_per_launch_mean"), "algorithmic_bytes_per_launch": BYTES_PER_CORR_FUSED * n,
+                       "traffic_source": "profiles/r02_nn_accum_16m.json (first 10 searches)" if prof16 else None}
     if world == 1:
         out.update({"value": out["single_gpu_value"], "ms_per_step": single["ms"], "parity": "n/a (one rank: nothing is sharded)"})
         return out
