@@ -1,23 +1,27 @@
 // icp_loop.cu -- the registration loop of MyICP::RegisterSymm (ICP/myicp.cpp:100-150) on device.
 //
-// One iteration = two kernels on the context stream:
+// One iteration = up to three kernels on the context stream:
+//   probe_kernel           (after a long step only) one budgeted single-query search per 256-query tile; its
+//                          neighbour seeds the whole tile in K1.
 //   nn_accum_kernel  (K1)  for every source point: apply the accumulated transform on load
 //                          (applyTransform, func.cpp:104-121, never materialised), exact nearest
 //                          neighbour in the target hierarchy (the search myicp.cpp:128-131 leaves
-//                          as a todo), evalDiff term (func.cpp:19-40), and the per-pair rows
+//                          as a todo) -- or the proof that the previous neighbour still stands (walk
+//                          skipping) --, evalDiff term (func.cpp:19-40), and the per-pair rows
 //                          m = (p+q) x n, n = n_p+n_q, c = (p-q).n of calculateMatrixNotation
 //                          (func.cpp:43-60) folded straight into the 27 unique normal-equation
 //                          sums (+ centroid, diff and count terms: 37 values), reduced by warp
-//                          shuffles and one fp64 partial row per block.
-//   solve_kernel     (K2)  fixed-order fp64 reduction of the partial rows, the loop test of
-//                          myicp.cpp:123, re-centring to the pair centroids, the 6x6 solve that
+//                          shuffles to one fp64 row per 256-query tile.
+//   solve_kernel     (K2)  canonical fp64 reduction of the tile rows (8 parts, fixed order: the result
+//                          does not depend on the grid, the batch or the number of GPUs), the loop
+//                          test of myicp.cpp:123, re-centring to the pair centroids, the 6x6 solve that
 //                          replaces the two JacobiSVD least-squares solves (func.cpp:64-73,87-88),
 //                          theta = atan|a| and the half-rotation composition (func.cpp:91-99, in
 //                          the order of the comment at :94), transform = incre * transform
-//                          (myicp.cpp:138).
-// The loop is one CUDA graph whose WHILE node repeats [K1,K2] until K2 clears the condition on the
-// device (default), or an unrolled graph of (max_iters+1) x [K1,K2] in which a device-side `done`
-// flag in SegState turns the remaining launches into early exits, or plain stream launches.
+//                          (myicp.cpp:138); decides probe / margin recording for the next search.
+// The loop is one CUDA graph whose WHILE node repeats [probe,K1,K2] until K2 clears the condition on
+// the device (default), or an unrolled graph of (max_iters+1) x [probe,K1,K2] in which a device-side
+// `done` flag in SegState turns the remaining launches into early exits, or plain stream launches.
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -1014,7 +1018,9 @@ int icp_loop_enqueue(icpsymm_ctx* ctx, int max_iters, float thr, const float* T_
     if ((rc = icp_reserve(ctx, &ctx->gsum, &ctx->gsum_cap, (size_t)nseg * ICP_PART_STRIDE))) return rc;
     if ((rc = icp_reserve(ctx, &ctx->gparts, &ctx->gparts_cap, (size_t)nseg * ICP_NPARTS * ICP_PART_STRIDE))) return rc;
     if ((rc = icp_reserve(ctx, &ctx->corr_pos, &ctx->corr_cap, (size_t)nseg * S.shape.pitch))) return rc;
-    const uint32_t hist_stride = (uint32_t)(single_search ? 1 : max_iters + 2);
+    // searches whose transform is kept per pair; a query's reference search is stored in 8 bits (K1 records margins only
+    // while the search index is below 255), so more history than that is never read
+    const uint32_t hist_stride = (uint32_t)(single_search ? 1 : (max_iters + 2 < 256 ? max_iters + 2 : 256));
     if ((rc = icp_reserve(ctx, &ctx->margin2, &ctx->margin_cap, (size_t)nseg * S.shape.pitch))) return rc;
     if ((rc = icp_reserve(ctx, &ctx->tile_seed, &ctx->tile_seed_cap, (size_t)nseg * bps))) return rc;
     if ((rc = icp_reserve(ctx, &ctx->ref_search, &ctx->ref_cap, (size_t)nseg * S.shape.pitch))) return rc;
@@ -1151,7 +1157,7 @@ int icp_loop_enqueue(icpsymm_ctx* ctx, int max_iters, float thr, const float* T_
 
     if (use_graph) {
         GraphKey key;
-        key.max_iters = max_iters; key.nseg = nseg; key.blocks_per_seg = bps;   // the parts follow from the shard
+        key.max_iters = max_iters; key.nseg = nseg; key.tiles_max = bps;   // the parts follow from the shard
         key.src_pitch = S.shape.pitch; key.tgt_pitch = T.shape.pitch;
         key.generation = ctx->generation;
         key.shard_rank = ctx->shard_rank; key.shard_world = ctx->shard_world; key.trace = ctx->opt_trace;

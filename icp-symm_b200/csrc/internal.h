@@ -40,13 +40,13 @@ struct CloudSet {
 
 struct GraphKey {
     int max_iters = -1;
-    uint32_t nseg = 0, blocks_per_seg = 0, src_pitch = 0, tgt_pitch = 0;
+    uint32_t nseg = 0, tiles_max = 0, src_pitch = 0, tgt_pitch = 0;
     // every device pointer the captured kernels hold belongs to this context; `generation` counts the
     // (re)allocations of all of them, so an unchanged generation means unchanged pointers
     unsigned long long generation = ~0ull;
     int mode = 0, shard_rank = 0, shard_world = 1, trace = 0, trace_stride = 0;   // mode: graph flavour + peer world
     bool operator==(const GraphKey& o) const {
-        return max_iters == o.max_iters && nseg == o.nseg && blocks_per_seg == o.blocks_per_seg &&
+        return max_iters == o.max_iters && nseg == o.nseg && tiles_max == o.tiles_max &&
                src_pitch == o.src_pitch && tgt_pitch == o.tgt_pitch && generation == o.generation && mode == o.mode &&
                shard_rank == o.shard_rank && shard_world == o.shard_world && trace == o.trace &&
                trace_stride == o.trace_stride;
