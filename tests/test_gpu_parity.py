@@ -299,7 +299,26 @@ def test_register_stream_mode_equals_graph_mode(ctx, cat, cat_out):
     assert np.array_equal(Tg, Tc) and sc["diff"] == sg["diff"]
 
 
-@pytest.mark.parametrize("case", ["cat", "synth200k", "noise_free"])
+def test_scheduling_and_seeding_options_never_change_a_result(ctx):
+    """tile order (most expensive first), probes (one seed per tile after a long step) and walk skipping only change HOW
+    the exact neighbours are found: every combination gives the same transform bits, diff and correspondences"""
+    src, tgt, _ = wl.config_synth(300_000)          # > 2 x 592 tiles: the ordered first search is active
+    ctx.set_source(src); ctx.set_target(tgt); ctx.estimate_normals(10)
+    ctx.set_option(icp.OPT_REL_DIFF_TOL, 1e-5)
+    out = []
+    try:
+        for order, probe, skip in ((1, 1, 1), (0, 1, 1), (1, 0, 1), (1, 1, 0), (0, 0, 0)):
+            ctx.set_option(icp.OPT_TILE_ORDER, order); ctx.set_option(icp.OPT_PROBE, probe); ctx.set_option(icp.OPT_SKIP_WALK, skip)
+            T, st, _ = ctx.register_symm(50, 1.0)
+            out.append((T.copy(), st["iters"], st["diff"], st["rmse"], ctx.get_correspondences()[0].copy()))
+    finally:
+        ctx.set_option(icp.OPT_TILE_ORDER, 1); ctx.set_option(icp.OPT_PROBE, 1); ctx.set_option(icp.OPT_SKIP_WALK, 1)
+        ctx.set_option(icp.OPT_REL_DIFF_TOL, 0.0)
+    for o in out[1:]:
+        assert np.array_equal(o[0], out[0][0]) and o[1:4] == out[0][1:4] and np.array_equal(o[4], out[0][4])
+
+
+@pytest.mark.parametrize("case", ["cat", "synth200k", "noise_free", "duplicates"])
 def test_skipping_walks_never_changes_a_result(ctx, cat, cat_out, case):
     """ICPSYMM_OPT_SKIP_WALK: a query whose winner provably stands keeps it without walking the index.  The proof is a
     margin argument about fp32 values, so the result must be IDENTICAL to always walking: transform bits, diff, rmse,
@@ -309,9 +328,16 @@ def test_skipping_walks_never_changes_a_result(ctx, cat, cat_out, case):
     elif case == "synth200k":
         src, tgt, _ = wl.config_synth(200_000)
         thr, rel, iters = 1.0, 1e-7, 14          # runs on long after convergence: many skipped searches
-    else:
+    elif case == "noise_free":
         src, tgt, _ = wl.config_synth(60_000, noise_frac=0.0)
         thr, rel, iters = 1e-9, 0.0, 10
+    else:
+        # every 5th target point exists twice (exact ties, the later copy must never win) and a block of source points
+        # coincides exactly with target points: zero distances, zero margins
+        src, tgt, Tt = wl.config_synth(40_000, deg=8.0, shift_frac=0.02)
+        tgt = np.concatenate([tgt, tgt[::5]])[np.random.default_rng(3).permutation(len(tgt) + len(tgt[::5]))]
+        src = src.copy(); src[:500] = orc.transform_points(np.linalg.inv(Tt).astype(np.float32), tgt[:500])
+        thr, rel, iters = 1e-9, 0.0, 9
     ctx.set_source(src); ctx.set_target(tgt); ctx.estimate_normals(10)
     ctx.set_option(icp.OPT_REL_DIFF_TOL, rel)
     ctx.set_option(icp.OPT_KERNEL_TIMING, 1)
