@@ -267,6 +267,7 @@ __global__ void __launch_bounds__(kNNThreads, kNNBlocksPerSM) probe_kernel(const
     const uint32_t tiles = icp_tiles(ns);
     const uint32_t tile = icp_shard_tile(tiles, P.part0, P.nparts, w - seg * P.work_per_seg);
     if (tile >= tiles || nt == 0) return;
+    ICP_ASSERT(tile < P.tiles_max);
     uint32_t i = tile * ICP_TILE + ICP_TILE / 2;
     if (i >= ns) i = ns - 1;
     const float4 s = ldg4(P.src.pts + (size_t)seg * P.src.shape.pitch + i);
@@ -346,7 +347,9 @@ __global__ void __launch_bounds__(kNNThreads, kNNBlocksPerSM) nn_accum_kernel(co
         // block-uniform; a finished pair has nothing to do and a smaller pair of a batch has fewer tiles
         const bool valid = !sDone && item0 + sub < P.work_per_seg && tile < tiles;
         float (*acc)[ICP_PART_STRIDE] = wacc[it & 1u][sub];
+        ICP_ASSERT(seg < P.src.nseg && (!valid || (size_t)tile * ICP_TILE < P.src.shape.pitch + ICP_TILE));
         if (valid) {
+        ICP_ASSERT(tile < P.tiles_max);
         const float4* __restrict__ spts = P.src.pts + (size_t)seg * P.src.shape.pitch;
         const float4* __restrict__ snrm = P.src.nrm + (size_t)seg * P.src.shape.pitch;
         const float4* __restrict__ tpts = P.tgt.pts + (size_t)seg * P.tgt.shape.pitch;
@@ -383,6 +386,7 @@ __global__ void __launch_bounds__(kNNThreads, kNNBlocksPerSM) nn_accum_kernel(co
                     if (sp < nt) best_offer(b, ldg4(tpts + sp), p.x, p.y, p.z);
                 }
                 const uint32_t ref = may_skip ? (uint32_t)P.ref_search[(size_t)seg * P.src.shape.pitch + i] : 0xffu;
+                ICP_ASSERT(ref == 0xffu || ref < sSearch);
                 if (ref < P.hist_stride && ref != 0xffu && prev < nt) {
                     const float3 xr = apply_rn(P.hist + ((size_t)seg * P.hist_stride + ref) * 12, s.x, s.y, s.z);
                     const float delta = __fsqrt_ru(dist2_rn(p.x, p.y, p.z, xr.x, xr.y, xr.z));
@@ -719,6 +723,7 @@ __global__ void __launch_bounds__(kSolveThreads) solve_kernel(const __grid_const
                 double s = 0.0;
                 const uint32_t part = P.part0 + ol;
                 const uint32_t own_blocks = icp_part_tiles(tiles, part);   // rows of this part: its tiles in curve order
+                ICP_ASSERT(part < ICP_NPARTS && (own_blocks == 0 || icp_part_tile(tiles, part, own_blocks - 1) < P.tiles_max));
                 const uint32_t C = icp_part_chunk(tiles), lc = 31u - (uint32_t)__clz((int)C);   // C is a power of two
                 const double* row = P.partial + (size_t)seg * P.tiles_max * ICP_PART_STRIDE + v;
                 for (uint32_t b = chain; b < own_blocks; b += ICP_K2_BATCH * kSolveParts) {
