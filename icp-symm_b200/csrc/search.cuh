@@ -123,7 +123,11 @@ __device__ __forceinline__ bool scan_leaf_lazy(const float4* __restrict__ seg_pt
 // when it is popped, before paying for a full visit.
 struct WarpPatch {
     float lox, loy, loz, hix, hiy, hiz;  // bounding box of the active lanes' queries (warp-uniform)
+    bool few;                            // at most ICP_FEW_LANES lanes are live
 };
+#ifndef ICP_FEW_LANES
+#define ICP_FEW_LANES 4
+#endif
 
 __device__ __forceinline__ float warp_min_f(float x) {
     return ordered_to_float(__reduce_min_sync(0xffffffffu, float_to_ordered(x)));
@@ -177,8 +181,15 @@ __device__ __forceinline__ uint32_t dense_children_test(const WideNode* __restri
 template <typename V>
 __device__ __forceinline__ uint32_t warp_node_test(const WideNode* __restrict__ nd, float qx, float qy, float qz,
                                                    uint32_t my_bound, bool active, const WarpPatch& pb,
-                                                   uint32_t max_bound, bool far_mode, int& pref, V& v) {
-    if (far_mode) {
+                                                   uint32_t max_bound, bool far_mode, int& pref, V& v,
+                                                   bool children_are_leaves = true) {
+    // A walk with only a few live lanes (the lanes of a unit that could not keep their winners, K1 skip test) is "far"
+    // by the patch criterion -- its patch is tiny -- but 32 exact tests per child are wasted on it: above the leaf
+    // parents the patch test alone selects nearly the same children (a superset; the extra ones are cut one level
+    // down) for a quarter of the instructions.  (For full packets in a far search the same shortcut costs 18 %: the
+    // largest bound of 32 lanes is a poor stand-in for each of them.)
+    const bool patch_only = far_mode && !children_are_leaves && pb.few;
+    if (far_mode && !patch_only) {
         uint32_t kmin, bb[ICP_FAN];
         const uint32_t mine = dense_children_test(nd, qx, qy, qz, my_bound, kmin, bb);
         pref = (int)(__reduce_min_sync(0xffffffffu, active ? kmin : 0xffffffffu) & 7u);
@@ -203,6 +214,10 @@ __device__ __forceinline__ uint32_t warp_node_test(const WideNode* __restrict__ 
     const uint32_t mask1 = __ballot_sync(0xffffffffu, pass1) & 0xffu;
     const uint32_t kmin1 = __reduce_min_sync(0xffffffffu, pass1 ? ((lbp & ~7u) | (uint32_t)cl) : 0xffffffffu);
     pref = (int)(kmin1 & 7u);
+    if (patch_only) {
+        if (V::kTrackMargin) v.prune(__reduce_min_sync(0xffffffffu, pass1 ? 0xffffffffu : lbp));
+        return mask1;
+    }
     // stage 2: exact, per lane, only for the survivors
     uint32_t mask2 = 0;
     if (__popc(mask1) >= ICP_DENSE_MIN) {
@@ -253,6 +268,7 @@ __device__ __forceinline__ void wide_traverse_group(const TreeShape& sh, const W
     WarpPatch pb;
     pb.lox = warp_min_f(active ? qx : inf);  pb.loy = warp_min_f(active ? qy : inf);  pb.loz = warp_min_f(active ? qz : inf);
     pb.hix = warp_max_f(active ? qx : -inf); pb.hiy = warp_max_f(active ? qy : -inf); pb.hiz = warp_max_f(active ? qz : -inf);
+    pb.few = __popc(__ballot_sync(0xffffffffu, active)) <= ICP_FEW_LANES;
     uint32_t max_bound = __reduce_max_sync(0xffffffffu, active ? v.bound_bits() : 0u);
     // far mode while the largest bound exceeds 4x the squared patch diagonal (both warp-uniform)
     const float pdx = pb.hix - pb.lox, pdy = pb.hiy - pb.loy, pdz = pb.hiz - pb.loz;
@@ -262,7 +278,7 @@ __device__ __forceinline__ void wide_traverse_group(const TreeShape& sh, const W
     uint32_t stale = 0;   // bit l: the pending mask of level l predates the latest bound improvement
     int l = top, pref;
     uint32_t i = 0;
-    uint32_t cur = warp_node_test(rec, qx, qy, qz, v.bound_bits(), active, pb, max_bound, far_mode, pref, v);
+    uint32_t cur = warp_node_test(rec, qx, qy, qz, v.bound_bits(), active, pb, max_bound, far_mode, pref, v, top == 1);
     unsigned long long saved = 0ull;   // byte l-1: pending mask of the open ancestor at level l
     for (;;) {
         if (V::kBudget && v.exhausted()) break;
@@ -290,7 +306,7 @@ __device__ __forceinline__ void wide_traverse_group(const TreeShape& sh, const W
             saved = (saved & ~(0xffull << sh8)) | ((unsigned long long)cur << sh8);
             --l; i = child;
             rec = seg_nodes + sh.level_off[l] + i;
-            cur = warp_node_test(rec, qx, qy, qz, v.bound_bits(), active, pb, max_bound, far_mode, pref, v);
+            cur = warp_node_test(rec, qx, qy, qz, v.bound_bits(), active, pb, max_bound, far_mode, pref, v, l == 1);
             stale &= ~(1u << l);
         }
         if (improved) {   // some active lane's bound improved (warp-uniform)
