@@ -124,6 +124,7 @@ __device__ __forceinline__ bool scan_leaf_lazy(const float4* __restrict__ seg_pt
 struct WarpPatch {
     float lox, loy, loz, hix, hiy, hiz;  // bounding box of the active lanes' queries (warp-uniform)
     bool few;                            // at most ICP_FEW_LANES lanes are live
+    bool single;                         // exactly one
 };
 #ifndef ICP_FEW_LANES
 #define ICP_FEW_LANES 4
@@ -188,7 +189,8 @@ __device__ __forceinline__ uint32_t warp_node_test(const WideNode* __restrict__ 
     // parents the patch test alone selects nearly the same children (a superset; the extra ones are cut one level
     // down) for a quarter of the instructions.  (For full packets in a far search the same shortcut costs 18 %: the
     // largest bound of 32 lanes is a poor stand-in for each of them.)
-    const bool patch_only = far_mode && !children_are_leaves && pb.few;
+    // With ONE live lane (the probe) the patch is that lane's query and the patch test is its exact test, at every level.
+    const bool patch_only = pb.single || (far_mode && !children_are_leaves && pb.few);
     if (far_mode && !patch_only) {
         uint32_t kmin, bb[ICP_FAN];
         const uint32_t mine = dense_children_test(nd, qx, qy, qz, my_bound, kmin, bb);
@@ -268,7 +270,11 @@ __device__ __forceinline__ void wide_traverse_group(const TreeShape& sh, const W
     WarpPatch pb;
     pb.lox = warp_min_f(active ? qx : inf);  pb.loy = warp_min_f(active ? qy : inf);  pb.loz = warp_min_f(active ? qz : inf);
     pb.hix = warp_max_f(active ? qx : -inf); pb.hiy = warp_max_f(active ? qy : -inf); pb.hiz = warp_max_f(active ? qz : -inf);
-    pb.few = __popc(__ballot_sync(0xffffffffu, active)) <= ICP_FEW_LANES;
+    {
+        const int live = __popc(__ballot_sync(0xffffffffu, active));
+        pb.few = live <= ICP_FEW_LANES;
+        pb.single = live == 1;
+    }
     uint32_t max_bound = __reduce_max_sync(0xffffffffu, active ? v.bound_bits() : 0u);
     // far mode while the largest bound exceeds 4x the squared patch diagonal (both warp-uniform)
     const float pdx = pb.hix - pb.lox, pdy = pb.hiy - pb.loy, pdz = pb.hiz - pb.loz;
