@@ -30,7 +30,9 @@ if os.path.exists(src):
 # 2. dominant kernel
 rep = os.path.join(G, "prof_nn_final.ncu-rep")
 if os.path.exists(rep):
-    rows = raw_csv(rep); h = {n: i for i, n in enumerate(rows[0])}; data = rows[2:]
+    rows = raw_csv(rep); h = {n: i for i, n in enumerate(rows[0])}
+    probe = [r for r in rows[2:] if "probe_kernel" in r[h["Kernel Name"]]]
+    data = [r for r in rows[2:] if "nn_accum" in r[h["Kernel Name"]]]      # the capture interleaves probe and search launches
     def col(name): return [float(r[h[name]].replace(",", "")) for r in data]
     unit = lambda name: rows[1][h[name]]
     def to_bytes(v, u): return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
@@ -38,6 +40,8 @@ if os.path.exists(rep):
     wr = [to_bytes(v, unit("dram__bytes_write.sum")) for v in col("dram__bytes_write.sum")]
     dur = col("gpu__time_duration.sum")
     summary = {
+        "probe_kernel_duration_" + unit("gpu__time_duration.sum"): [float(r[h["gpu__time_duration.sum"]].replace(",", "")) for r in probe],
+        "probe_kernel_warp_inst": [float(r[h["smsp__inst_executed.sum"]].replace(",", "")) for r in probe],
         "kernel": "nn_accum_kernel", "points": 1000000,
         "capture": "ncu --set full --clock-control none, every search of one 1M-point registration "
                    "(far, mid, near, then converged ones that mostly skip their walks); cold-cache, serialised",
@@ -56,14 +60,15 @@ if os.path.exists(rep):
         "pipe_fma_pct": col("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active"),
     }
     json.dump(summary, open(os.path.join(OUT, RND + "_nn_accum.json"), "w"), indent=1)
-    open("/tmp/_raw.csv", "w").write(sh(f"ncu -i {rep} --page raw --csv 2>/dev/null"))
+    with open("/tmp/_raw.csv", "w", newline="") as f_:
+        csv.writer(f_).writerows(rows[:2] + data)
     open(os.path.join(OUT, RND + "_nn_accum_ncu_metrics.txt"), "w").write(
         "# nn_accum_kernel, ncu --set full --clock-control none --import-source on, all searches of one 1M registration\n"
         "# (columns: far first search, second, third, then the converged ones)\n" + sh(f"python {ROOT}/tools/ncu_key_metrics.py /tmp/_raw.csv"))
     open("/tmp/_src.csv", "w").write(sh(f"ncu -i {rep} --page source --print-source cuda,sass --csv 2>/dev/null"))
     open(os.path.join(OUT, RND + "_nn_accum_source_hotspots.txt"), "w").write(
-        "# executed warp-instructions and stall samples per CUDA source line (far launch 0, converged launch 3)\n"
-        + sh(f"python {ROOT}/tools/ncu_source_lines.py /tmp/_src.csv 0 3"))
+        "# executed warp-instructions and stall samples per CUDA source line; launches of the capture: 0 probe, 1 far first search,\n# 2 probe, 3 second search, 4 (idle probe), 5 third, 6, 7 fourth (the first that records margins)\n"
+        + sh(f"python {ROOT}/tools/ncu_source_lines.py /tmp/_src.csv 1 3 7"))
     # the walk itself is an out-of-line device function: its SASS is listed under nn_walk
 
 # 2b. the 16M pair (working set far beyond L2: the DRAM-bound configuration)
