@@ -16,6 +16,9 @@ with icp.Context(0) as ctx:
     for _ in range(2):
         idx, d2 = ctx.find_correspondences()
     tiles = (n + 255) // 256
+    if hasattr(L, "icpsymm_debug_heavy"):
+        L.icpsymm_debug_heavy.argtypes = [C.c_void_p]
+        print("heavy tiles (walked in shares):", L.icpsymm_debug_heavy(ctx.h))
     tt = np.zeros(2 * tiles, np.uint64)
     L.icpsymm_debug_tile_times(tt.ctypes.data_as(C.c_void_p), tiles)
     sp = np.zeros((((n + 7) // 8) * 8, 4), np.float32)
@@ -27,6 +30,18 @@ with icp.Context(0) as ctx:
     dur = (t1 - t0) * 1e-3
     start = (t0 - t0.min()) * 1e-3
     md = np.array([d[k * 256:(k + 1) * 256].mean() for k in range(tiles)])
+    mx = np.array([d[k * 256:(k + 1) * 256].max() for k in range(tiles)])
+    mn = np.array([d[k * 256:(k + 1) * 256].min() for k in range(tiles)])
+    xyz = sp[:n, :3]
+    diag = np.array([np.linalg.norm(xyz[k * 256:(k + 1) * 256].max(0) - xyz[k * 256:(k + 1) * 256].min(0)) for k in range(tiles)])
+    udiag = np.array([max(np.linalg.norm(xyz[u * 32:(u + 1) * 32].max(0) - xyz[u * 32:(u + 1) * 32].min(0)) for u in range(k * 8, min(k * 8 + 8, (n + 31) // 32))) for k in range(tiles)])
+    for name, f in (("mean d", md), ("max d", mx), ("min d", mn), ("tile diag", diag), ("max unit diag", udiag), ("max d * unit diag", mx * udiag)):
+        print(f"corr(duration, {name}) = {np.corrcoef(dur, f)[0, 1]:.3f}")
+    top = np.argsort(-dur)[:12]
+    print("slowest tiles: idx start dur mean_d max_d tile_diag max_unit_diag")
+    for k in top:
+        print(k, round(start[k], 1), round(dur[k], 1), round(md[k], 3), round(mx[k], 3), round(diag[k], 3), round(udiag[k], 3))
+    print("medians:", np.median(dur), np.median(md), np.median(diag), np.median(udiag))
     print("kernel span us", (t1.max() - t0.min()) * 1e-3, "sum of tile durations / 592 us", dur.sum() / 592)
     print("corr(duration, mean NN distance)", np.corrcoef(dur, md)[0, 1])
     print("tile  start_us  dur_us  mean_dist   (every 100th tile)")
