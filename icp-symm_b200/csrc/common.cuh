@@ -229,6 +229,20 @@ __host__ __device__ __forceinline__ float ordered_to_float(uint32_t u) {
 
 __device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
 
+// Two consecutive float4 (32-byte aligned) with ONE 256-bit read-only load (sm_100: LDG.E.ENL2.256): a leaf group is
+// four loads instead of eight, a node record six instead of twelve -- the walks are issue-bound, and every load of a
+// warp-uniform address also costs the two moves that bring the address out of the uniform registers.
+struct float4x2 {
+    float4 a, b;
+};
+__device__ __forceinline__ float4x2 ldg8(const float4* p) {
+    float4x2 r;
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(r.a.x), "=f"(r.a.y), "=f"(r.a.z), "=f"(r.a.w), "=f"(r.b.x), "=f"(r.b.y), "=f"(r.b.z), "=f"(r.b.w)
+        : "l"(p));
+    return r;
+}
+
 #define ICP_CUDA_CHECK(expr)                                                        \
     do {                                                                            \
         cudaError_t _e = (expr);                                                    \

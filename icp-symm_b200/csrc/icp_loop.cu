@@ -29,6 +29,15 @@
 #include <cub/device/device_radix_sort.cuh>
 
 #include "internal.h"
+#ifndef ICP_WIDE_LEAF
+#define ICP_WIDE_LEAF 1   // 256-bit loads in the walks of this translation unit (search.cuh)
+#endif
+#ifndef ICP_WIDE_NODE
+#define ICP_WIDE_NODE 1
+#endif
+#ifndef ICP_BOUND_CACHE
+#define ICP_BOUND_CACHE 0   // re-test stale leaf groups from a shared-memory cache of the lanes' bounds (search.cuh): measured, no gain
+#endif
 #include "search.cuh"
 
 #ifdef ICP_BLOCK_TIMES   // developer instrumentation: per-block start/end/SM of the last K1 launch
@@ -307,7 +316,15 @@ __global__ void __launch_bounds__(kNNThreads, kNNBlocksPerSM) nn_accum_kernel(co
     __shared__ int sTrack;            // walks of this search record margins (K2 expects the next step to be small)
     __shared__ int sProbe;            // the probe kernel has left one seed per tile
     __shared__ uint32_t sWork[2];
+#if ICP_BOUND_CACHE
+    __shared__ uint32_t sBoundCache[ICP_FAN * kNNThreads];   // [warp][child][lane], see warp_node_test
+#endif
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#if ICP_BOUND_CACHE
+    uint32_t* const lbc = sBoundCache + warp * (ICP_FAN * 32) + lane;
+#else
+    uint32_t* const lbc = nullptr;
+#endif
     const LoopParams lp = *P.lp;
     uint32_t cur_seg = 0xffffffffu;
     // tickets 0 .. gridDim-1 are implicit (the counter starts at gridDim); the ticket of the NEXT tile is drawn
@@ -372,6 +389,11 @@ __global__ void __launch_bounds__(kNNThreads, kNNBlocksPerSM) nn_accum_kernel(co
         // oracle compares (a tie has zero margin and never keeps).
         const bool may_skip = lp.skip_walk && lp.warm_start && !lp.identity_pairs;
         bool keep = false;   // this lane's winner provably stands
+        // the previous correspondent and its normal: a lane that keeps its winner accumulates with them as they are,
+        // without the two dependent gathers (inverse permutation, then point and normal) -- the searches in which most
+        // lanes keep are bound by exactly that chain of loads
+        uint32_t prev = 0xffffffffu;
+        float4 sq = make_float4(0.f, 0.f, 0.f, 0.f), snq = sq, sn0 = sq;
         if (active) {
             const float4 s = ldg4(spts + i);
             p = apply_rn(sT, s.x, s.y, s.z);
@@ -379,8 +401,8 @@ __global__ void __launch_bounds__(kNNThreads, kNNBlocksPerSM) nn_accum_kernel(co
                 uint32_t pos = P.tgt.pos_of_orig[(size_t)seg * P.tgt.shape.pitch + __float_as_uint(s.w)];
                 best_offer(b, ldg4(tpts + pos), p.x, p.y, p.z);
             } else {
-                uint32_t prev = lp.warm_start ? corr[i] : 0xffffffffu;
-                if (prev < nt) best_offer(b, ldg4(tpts + prev), p.x, p.y, p.z);
+                prev = lp.warm_start ? corr[i] : 0xffffffffu;
+                if (prev < nt) { sq = ldg4(tpts + prev); best_offer(b, sq, p.x, p.y, p.z); }
                 if (sProbe) {   // the neighbour of the tile's middle query (probe_kernel): a good first bound for all 256
                     const uint32_t sp = P.tile_seed[(size_t)seg * P.tiles_max + tile];
                     if (sp < nt) best_offer(b, ldg4(tpts + sp), p.x, p.y, p.z);
@@ -388,6 +410,8 @@ __global__ void __launch_bounds__(kNNThreads, kNNBlocksPerSM) nn_accum_kernel(co
                 const uint32_t ref = may_skip ? (uint32_t)P.ref_search[(size_t)seg * P.src.shape.pitch + i] : 0xffu;
                 ICP_ASSERT(ref == 0xffu || ref < sSearch);
                 if (ref < P.hist_stride && ref != 0xffu && prev < nt) {
+                    snq = ldg4(tnrm + prev);   // issued with the loads of the test, used only if the lane keeps
+                    sn0 = ldg4(snrm + i);
                     const float3 xr = apply_rn(P.hist + ((size_t)seg * P.hist_stride + ref) * 12, s.x, s.y, s.z);
                     const float delta = __fsqrt_ru(dist2_rn(p.x, p.y, p.z, xr.x, xr.y, xr.z));
                     const float d1 = __fsqrt_ru(b.d2());
@@ -400,33 +424,40 @@ __global__ void __launch_bounds__(kNNThreads, kNNBlocksPerSM) nn_accum_kernel(co
         // are bystanders (split units, see finish_units_kernel in index_build.cu, are not walked per cluster here:
         // wrapping this walk in a pass loop costs the common case 15 %, far more than the rare split unit costs)
         const bool walk = active && !keep;
+        // the winner's sorted position, point and normal.  A unit that walks looks them up afterwards (the key carries the
+        // original index; the sorted position comes from the inverse permutation); in a unit that does not walk -- every
+        // lane keeps, or identity pairing -- a keeping lane already holds all three (nothing of it is live across the walk)
+        uint32_t bpos = 0xffffffffu;
+        float4 q = make_float4(0.f, 0.f, 0.f, 0.f), nq = q, n0 = q;
+        auto look_up = [&]() {
+            bpos = (b.id() != (uint32_t)ICP_INVALID_ID) ? __ldg(P.tgt.pos_of_orig + (size_t)seg * P.tgt.shape.pitch + b.id())
+                                                        : 0xffffffffu;
+            ICP_ASSERT(bpos == 0xffffffffu || bpos < nt);
+            corr[i] = bpos;
+            if (bpos < nt) { q = ldg4(tpts + bpos); nq = ldg4(tnrm + bpos); n0 = ldg4(snrm + i); }
+        };
         if (!lp.identity_pairs && nt > 0 && __any_sync(0xffffffffu, walk)) {
             uint8_t* ref_slot = P.ref_search + (size_t)seg * P.src.shape.pitch + i;
             if (sTrack && may_skip && sSearch < 0xffu) {
-                const WalkResult r = nn_walk<true>(&P.tgt.shape, tbox, tpts, p.x, p.y, p.z, walk, b.key);
+                const WalkResult r = nn_walk<true>(&P.tgt.shape, tbox, tpts, p.x, p.y, p.z, walk, b.key, lbc);
                 b.key = r.key;
                 if (walk) { P.margin2[(size_t)seg * P.src.shape.pitch + i] = __uint_as_float(r.m2); *ref_slot = (uint8_t)sSearch; }
             } else {
-                const WalkResult r = nn_walk<false>(&P.tgt.shape, tbox, tpts, p.x, p.y, p.z, walk, b.key);
+                const WalkResult r = nn_walk<false>(&P.tgt.shape, tbox, tpts, p.x, p.y, p.z, walk, b.key, lbc);
                 b.key = r.key;
                 if (walk && may_skip) *ref_slot = 0xffu;   // walked without tracking: the old margin belongs to another winner
             }
+            if (active) look_up();
+        } else if (active) {
+            if (keep && b.id() == __float_as_uint(sq.w)) { bpos = prev; q = sq; nq = snq; n0 = sn0; }   // corr[i] already holds it
+            else look_up();
         }
         float v[40];   // declared after the walk so that none of it is live across it; ICP_NSUMS = 37 used
 #pragma unroll
         for (int k = 0; k < 40; k++) v[k] = 0.f;
         if (active) {
-            // the key carries the original index; the sorted position comes from the inverse permutation
-            const uint32_t bpos = (b.id() != (uint32_t)ICP_INVALID_ID)
-                                      ? __ldg(P.tgt.pos_of_orig + (size_t)seg * P.tgt.shape.pitch + b.id())
-                                      : 0xffffffffu;
             const float bd2 = b.d2();
-            ICP_ASSERT(bpos == 0xffffffffu || bpos < nt);
-            corr[i] = bpos;
             if (bpos < nt) {
-                const float4 q = ldg4(tpts + bpos);
-                const float4 nq = ldg4(tnrm + bpos);
-                const float4 n0 = ldg4(snrm + i);
                 const float3 np = rotate_rn(sT, n0.x, n0.y, n0.z);
                 v[33] = __fsqrt_rn(bd2);
                 v[34] = bd2;

@@ -26,6 +26,33 @@
 #define ICP_DENSE_MIN 4                  // stage-1 survivors from which the all-children exact test is cheaper than per-child shuffles
 #endif
 
+// 256-bit loads (common.cuh: ldg8) for the leaf groups / the node records; a translation unit chooses before including
+// this header (K1 gains 4-6 % per search; the normals kernel, at 72 registers, starts to spill with them)
+#ifndef ICP_WIDE_LEAF
+#define ICP_WIDE_LEAF 0
+#endif
+#ifndef ICP_WIDE_NODE
+#define ICP_WIDE_NODE 0
+#endif
+__device__ __forceinline__ void load_leaf_group(const float4* __restrict__ lp, float4 (&c)[ICP_LEAF]) {
+#if ICP_WIDE_LEAF
+#pragma unroll
+    for (int j = 0; j < ICP_LEAF; j += 2) { const float4x2 t = ldg8(lp + j); c[j] = t.a; c[j + 1] = t.b; }
+#else
+#pragma unroll
+    for (int j = 0; j < ICP_LEAF; j++) c[j] = ldg4(lp + j);
+#endif
+}
+__device__ __forceinline__ void load_node_record(const float4* __restrict__ p4, float4 (&r)[12]) {
+#if ICP_WIDE_NODE
+#pragma unroll
+    for (int j = 0; j < 12; j += 2) { const float4x2 t = ldg8(p4 + j); r[j] = t.a; r[j + 1] = t.b; }
+#else
+#pragma unroll
+    for (int j = 0; j < 12; j++) r[j] = ldg4(p4 + j);
+#endif
+}
+
 // best candidate so far as ONE 64-bit key, (d2 bits << 32) | original index: d2 >= 0, so unsigned
 // integer order on the key is exactly the (d2, lowest original index) order the oracle defines, and
 // an update is a 64-bit min (two compares, two selects) instead of a three-way predicate.
@@ -54,8 +81,7 @@ __device__ __forceinline__ void scan_leaf(const float4* __restrict__ seg_pts, ui
                                           float qz, Best& b) {
     const float4* lp = seg_pts + (size_t)g * ICP_LEAF;
     float4 c[ICP_LEAF];
-#pragma unroll
-    for (int j = 0; j < ICP_LEAF; j++) c[j] = ldg4(lp + j);
+    load_leaf_group(lp, c);
     const NegQuery nq = make_neg_query(qx, qy, qz);
 #pragma unroll
     for (int j = 0; j < ICP_LEAF; j++) best_offer_packed(b, c[j], nq);
@@ -76,8 +102,7 @@ __device__ __forceinline__ bool scan_leaf_lazy(const float4* __restrict__ seg_pt
     const float4* lp = seg_pts + (size_t)g * ICP_LEAF;
     float4 c[ICP_LEAF];
     float d[ICP_LEAF];
-#pragma unroll
-    for (int j = 0; j < ICP_LEAF; j++) c[j] = ldg4(lp + j);
+    load_leaf_group(lp, c);
 #pragma unroll
     for (int j = 0; j < ICP_LEAF; j++) d[j] = dist2_packed(nq, c[j]);
     const float m = fminf(fminf(fminf(d[0], d[1]), fminf(d[2], d[3])), fminf(fminf(d[4], d[5]), fminf(d[6], d[7])));
@@ -137,6 +162,11 @@ __device__ __forceinline__ float warp_max_f(float x) {
     return ordered_to_float(__reduce_max_sync(0xffffffffu, float_to_ordered(x)));
 }
 
+// A box is entered when its bound does not exceed the lane's bound AND is finite (padding boxes have bound +inf and
+// a lane without a candidate yet has bound +inf).  Capping the lane's bound at the largest finite float turns the
+// two comparisons per box into one.
+__device__ __forceinline__ uint32_t bound_cap(uint32_t bound_bits) { return min(bound_bits, ICP_INF_BITS - 1u); }
+
 __device__ __forceinline__ uint32_t point_box_bits(float lx, float ly, float lz, float hx, float hy, float hz,
                                                    float qx, float qy, float qz) {
     float ex = fmaxf(fmaxf(__fsub_rn(lx, qx), __fsub_rn(qx, hx)), 0.f);
@@ -152,10 +182,10 @@ __device__ __forceinline__ uint32_t dense_children_test(const WideNode* __restri
                                                         uint32_t my_bound, uint32_t& kmin, uint32_t (&bb)[ICP_FAN]) {
     const float4* p4 = reinterpret_cast<const float4*>(nd);
     float4 r[12];
-#pragma unroll
-    for (int j = 0; j < 12; j++) r[j] = ldg4(p4 + j);
+    load_node_record(p4, r);
     uint32_t mine = 0;
     kmin = 0xffffffffu;
+    my_bound = bound_cap(my_bound);
     const NegQuery nq = make_neg_query(qx, qy, qz);
 #pragma unroll
     for (int h = 0; h < 2; h++) {
@@ -166,7 +196,7 @@ __device__ __forceinline__ uint32_t dense_children_test(const WideNode* __restri
                     r[8 + h].z, r[8 + h].w, r[10 + h].z, r[10 + h].w, nq, b[2], b[3]);
 #pragma unroll
         for (int c = 0; c < 4; c++) {
-            const bool pass = b[c] <= my_bound && b[c] != ICP_INF_BITS;
+            const bool pass = b[c] <= my_bound;
             bb[4 * h + c] = b[c];
             mine |= pass ? (1u << (4 * h + c)) : 0u;
             kmin = min(kmin, pass ? ((b[c] & ~7u) | (uint32_t)(4 * h + c)) : 0xffffffffu);
@@ -183,7 +213,13 @@ template <typename V>
 __device__ __forceinline__ uint32_t warp_node_test(const WideNode* __restrict__ nd, float qx, float qy, float qz,
                                                    uint32_t my_bound, bool active, const WarpPatch& pb,
                                                    uint32_t max_bound, bool far_mode, int& pref, V& v,
-                                                   bool children_are_leaves = true) {
+                                                   bool children_are_leaves, bool& cached) {
+    // BOUND CACHE (V::kBoundCache).  A lane's lower bound of a child box depends on the query and the box only, not on
+    // the lane's current bound.  When the children are leaf groups the warp stays at this node until all of them are
+    // popped, so the bounds computed here are parked in a per-lane shared-memory column (v.lbc[c * 32]) and a stale
+    // child is re-tested by ONE shared load instead of six global loads and the box arithmetic.  `cached` tells
+    // whether every admitted child has its entry (the patch-only shortcut computes no per-lane bounds).
+    cached = false;
     // A walk with only a few live lanes (the lanes of a unit that could not keep their winners, K1 skip test) is "far"
     // by the patch criterion -- its patch is tiny -- but 32 exact tests per child are wasted on it: above the leaf
     // parents the patch test alone selects nearly the same children (a superset; the extra ones are cut one level
@@ -196,6 +232,11 @@ __device__ __forceinline__ uint32_t warp_node_test(const WideNode* __restrict__ 
         const uint32_t mine = dense_children_test(nd, qx, qy, qz, my_bound, kmin, bb);
         pref = (int)(__reduce_min_sync(0xffffffffu, active ? kmin : 0xffffffffu) & 7u);
         const uint32_t mask = __reduce_or_sync(0xffffffffu, active ? mine : 0u);
+        if (V::kBoundCache && children_are_leaves) {
+#pragma unroll
+            for (int c = 0; c < ICP_FAN; c++) v.lbc[c * 32] = bb[c];
+            cached = true;
+        }
         if (V::kTrackMargin) {
 #pragma unroll
             for (int c = 0; c < ICP_FAN; c++) v.prune(((mask >> c) & 1u) ? 0xffffffffu : bb[c]);
@@ -226,6 +267,11 @@ __device__ __forceinline__ uint32_t warp_node_test(const WideNode* __restrict__ 
         uint32_t kmin, bb[ICP_FAN];
         const uint32_t mine = dense_children_test(nd, qx, qy, qz, my_bound, kmin, bb);
         mask2 = __reduce_or_sync(0xffffffffu, active ? mine : 0u) & mask1;
+        if (V::kBoundCache && children_are_leaves) {
+#pragma unroll
+            for (int c = 0; c < ICP_FAN; c++) v.lbc[c * 32] = bb[c];
+            cached = true;
+        }
         if (V::kTrackMargin) {
 #pragma unroll
             for (int c = 0; c < ICP_FAN; c++) v.prune(((mask2 >> c) & 1u) ? 0xffffffffu : bb[c]);
@@ -239,9 +285,12 @@ __device__ __forceinline__ uint32_t warp_node_test(const WideNode* __restrict__ 
             const float lz = __shfl_sync(0xffffffffu, blz, c), hx = __shfl_sync(0xffffffffu, bhx, c);
             const float hy = __shfl_sync(0xffffffffu, bhy, c), hz = __shfl_sync(0xffffffffu, bhz, c);
             const uint32_t lb = point_box_bits(lx, ly, lz, hx, hy, hz, qx, qy, qz);
-            if (__any_sync(0xffffffffu, active && lb <= my_bound && lb != ICP_INF_BITS)) mask2 |= 1u << c;
-            else if (V::kTrackMargin) v.prune(lb);
+            if (__any_sync(0xffffffffu, active && lb <= my_bound && lb != ICP_INF_BITS)) {
+                mask2 |= 1u << c;
+                if (V::kBoundCache && children_are_leaves) v.lbc[c * 32] = lb;
+            } else if (V::kTrackMargin) v.prune(lb);
         }
+        cached = V::kBoundCache && children_are_leaves;
     }
     return mask2;
 }
@@ -254,6 +303,15 @@ __device__ __forceinline__ bool warp_child_recheck(const WideNode* __restrict__ 
     const uint32_t lb = point_box_bits(__ldg(f), __ldg(f + 8), __ldg(f + 16), __ldg(f + 24), __ldg(f + 32),
                                        __ldg(f + 40), qx, qy, qz);
     const bool enter = __any_sync(0xffffffffu, active && lb <= my_bound && lb != ICP_INF_BITS);
+    if (V::kTrackMargin && !enter) v.prune(lb);
+    return enter;
+}
+
+// the same re-test from the bound cache (see warp_node_test)
+template <typename V>
+__device__ __forceinline__ bool warp_child_recheck_cached(int c, uint32_t my_bound, bool active, V& v) {
+    const uint32_t lb = v.lbc[c * 32];
+    const bool enter = __any_sync(0xffffffffu, active && lb <= bound_cap(my_bound));
     if (V::kTrackMargin && !enter) v.prune(lb);
     return enter;
 }
@@ -284,7 +342,8 @@ __device__ __forceinline__ void wide_traverse_group(const TreeShape& sh, const W
     uint32_t stale = 0;   // bit l: the pending mask of level l predates the latest bound improvement
     int l = top, pref;
     uint32_t i = 0;
-    uint32_t cur = warp_node_test(rec, qx, qy, qz, v.bound_bits(), active, pb, max_bound, far_mode, pref, v, top == 1);
+    bool cached;   // the bound cache covers the pending children of the current level-1 node
+    uint32_t cur = warp_node_test(rec, qx, qy, qz, v.bound_bits(), active, pb, max_bound, far_mode, pref, v, top == 1, cached);
     unsigned long long saved = 0ull;   // byte l-1: pending mask of the open ancestor at level l
     for (;;) {
         if (V::kBudget && v.exhausted()) break;
@@ -300,7 +359,11 @@ __device__ __forceinline__ void wide_traverse_group(const TreeShape& sh, const W
         const int c = (pref >= 0 && ((cur >> pref) & 1u)) ? pref : (__ffs((int)cur) - 1);
         pref = -1;
         cur &= ~(1u << c);
-        if (((stale >> l) & 1u) && !warp_child_recheck(rec, c, qx, qy, qz, v.bound_bits(), active, v)) continue;
+        if ((stale >> l) & 1u) {
+            const bool enter = (V::kBoundCache && l == 1 && cached) ? warp_child_recheck_cached(c, v.bound_bits(), active, v)
+                                                                    : warp_child_recheck(rec, c, qx, qy, qz, v.bound_bits(), active, v);
+            if (!enter) continue;
+        }
         const uint32_t child = (i << ICP_LOG_FAN) + (uint32_t)c;
         ICP_ASSERT(l >= 1 && l <= top && i < sh.level_cnt[l] && child < sh.level_cnt[l - 1]);
         bool improved = false;
@@ -312,7 +375,7 @@ __device__ __forceinline__ void wide_traverse_group(const TreeShape& sh, const W
             saved = (saved & ~(0xffull << sh8)) | ((unsigned long long)cur << sh8);
             --l; i = child;
             rec = seg_nodes + sh.level_off[l] + i;
-            cur = warp_node_test(rec, qx, qy, qz, v.bound_bits(), active, pb, max_bound, far_mode, pref, v, l == 1);
+            cur = warp_node_test(rec, qx, qy, qz, v.bound_bits(), active, pb, max_bound, far_mode, pref, v, l == 1, cached);
             stale &= ~(1u << l);
         }
         if (improved) {   // some active lane's bound improved (warp-uniform)
@@ -345,10 +408,11 @@ __device__ __forceinline__ void wide_traverse_warp(const TreeShape& sh, const Wi
 // pinned fp32 arithmetic (a box bound never exceeds the fp32 distance of a member point).  K1 stores it and uses it
 // in later searches: while the query has moved by less than the gap between the winner's distance and the margin,
 // the winner cannot have changed and the walk is skipped (icp_loop.cu).
-template <bool TRACK, bool BUDGET = false>
+template <bool TRACK, bool BUDGET = false, bool CACHE = false>
 struct NNVisitor {
     static constexpr bool kTrackMargin = TRACK;
     static constexpr bool kBudget = BUDGET;   // the walk may stop early (probe: any real point is a useful seed)
+    static constexpr bool kBoundCache = CACHE;
     int budget = 0;                           // leaf scans left
     __device__ __forceinline__ bool exhausted() const { return BUDGET && budget <= 0; }
     Best& b;
@@ -356,6 +420,7 @@ struct NNVisitor {
     float qx, qy, qz;
     NegQuery nq;
     uint32_t m2;
+    uint32_t* lbc;                            // this lane's column of the bound cache (shared memory, stride 32), or null
     __device__ __forceinline__ uint32_t bound_bits() const { return (uint32_t)(b.key >> 32); }
     __device__ __forceinline__ void set_active(bool) {}
     __device__ __forceinline__ void prune(uint32_t lower_bound_bits) { if (TRACK) m2 = min(m2, lower_bound_bits); }
@@ -371,17 +436,21 @@ struct NNVisitor {
 // Out-of-line entry of the walk: its own register allocation, so that the margin-tracking flavour (more live
 // state) does not tax the lean one when a kernel holds both.
 struct WalkResult { unsigned long long key; uint32_t m2; };
+#ifndef ICP_BOUND_CACHE
+#define ICP_BOUND_CACHE 0   // a translation unit whose walks get a shared-memory column per lane defines it to 1
+#endif
 template <bool TRACK>
 __device__ __forceinline__ uint32_t nn_traverse_warp(const TreeShape& sh, const WideNode* __restrict__ seg_nodes,
                                                      const float4* __restrict__ seg_pts, float qx, float qy, float qz,
-                                                     bool active, uint32_t split_mask, Best& b);
+                                                     bool active, uint32_t split_mask, Best& b, uint32_t* lbc = nullptr);
+// lbc: this lane's column of the bound cache (8 words, stride 32, shared memory); used when ICP_BOUND_CACHE
 template <bool TRACK>
 __device__ __noinline__ WalkResult nn_walk(const TreeShape* sh, const WideNode* __restrict__ seg_nodes,
                                            const float4* __restrict__ seg_pts, float qx, float qy, float qz, bool active,
-                                           unsigned long long key) {
+                                           unsigned long long key, uint32_t* lbc) {
     Best b; b.key = key;
     WalkResult r;
-    r.m2 = nn_traverse_warp<TRACK>(*sh, seg_nodes, seg_pts, qx, qy, qz, active, 0u, b);
+    r.m2 = nn_traverse_warp<TRACK>(*sh, seg_nodes, seg_pts, qx, qy, qz, active, 0u, b, lbc);
     r.key = b.key;
     return r;
 }
@@ -390,8 +459,8 @@ __device__ __noinline__ WalkResult nn_walk(const TreeShape* sh, const WideNode* 
 template <bool TRACK>
 __device__ __forceinline__ uint32_t nn_traverse_warp(const TreeShape& sh, const WideNode* __restrict__ seg_nodes,
                                                      const float4* __restrict__ seg_pts, float qx, float qy, float qz,
-                                                     bool active, uint32_t split_mask, Best& b) {
-    NNVisitor<TRACK> v{0, b, seg_pts, qx, qy, qz, make_neg_query(qx, qy, qz), TRACK ? ICP_INF_BITS : 0u};
+                                                     bool active, uint32_t split_mask, Best& b, uint32_t* lbc) {
+    NNVisitor<TRACK, false, ICP_BOUND_CACHE != 0> v{0, b, seg_pts, qx, qy, qz, make_neg_query(qx, qy, qz), TRACK ? ICP_INF_BITS : 0u, lbc};
     wide_traverse_warp(sh, seg_nodes, qx, qy, qz, active, split_mask, v);
     return v.m2;
 }
@@ -402,7 +471,7 @@ static __device__ __noinline__ unsigned long long nn_walk_budget(const TreeShape
                                                           const float4* __restrict__ seg_pts, float qx, float qy, float qz,
                                                           bool active, unsigned long long key, int budget) {
     Best b; b.key = key;
-    NNVisitor<false, true> v{budget, b, seg_pts, qx, qy, qz, make_neg_query(qx, qy, qz), 0u};
+    NNVisitor<false, true> v{budget, b, seg_pts, qx, qy, qz, make_neg_query(qx, qy, qz), 0u, nullptr};
     wide_traverse_warp(*sh, seg_nodes, qx, qy, qz, active, 0u, v);
     return b.key;
 }
@@ -420,6 +489,21 @@ static __device__ __noinline__ unsigned long long nn_walk_budget(const TreeShape
 //            is removed until k are left -- the oracle's tie rule, lowest original index first.
 // After a final flush + compact the column holds exactly the k nearest neighbours.
 // EXACT = the list is used with k == KMAX (the reference's k = 10, myicp.cpp:160).
+// out of line on purpose: it almost never runs, and inlined at every compaction it was a quarter of the normals kernel's code
+static __device__ __noinline__ int knn_drop_ties(unsigned long long* buf, int stride, int w, int k, const float4* __restrict__ pts) {
+    while (w > k) {
+        int worst = 0;
+        unsigned long long worst_key = 0ull;
+        for (int r = 0; r < w; r++) {
+            const unsigned long long e = buf[r * stride];
+            const unsigned long long key = (e & 0xffffffff00000000ull) | __float_as_uint(ldg4(pts + (uint32_t)e).w);
+            if (key >= worst_key) { worst_key = key; worst = r; }
+        }
+        w--;
+        buf[worst * stride] = buf[w * stride];
+    }
+    return w;
+}
 #define ICP_KNN_UNFILLED 0xfffffffeu     // above every distance, below the 0xffffffff of padding points
 template <int KMAX, bool EXACT>
 struct KList {
@@ -469,27 +553,19 @@ struct KList {
     }
     __device__ __forceinline__ void compact(int k, const float4* __restrict__ pts) {
         const int n = __reduce_max_sync(0xffffffffu, cnt);
+        // branch-free: every lane reads slot r (r < n <= CAP, so the slot exists; what a lane reads beyond its own
+        // count is ignored) and keeps it under a predicate; the survivors stay in their order
+        unsigned long long* wp = buf;
+        const unsigned long long* rp = buf;
         int w = 0;
-#pragma unroll 4
-        for (int r = 0; r < n; r++) {
-            if (r < cnt) {
-                const unsigned long long e = buf[r * stride];
-                if ((uint32_t)(e >> 32) <= kth) { buf[w * stride] = e; w++; }
-            }
+#pragma unroll 2
+        for (int r = 0; r < n; r++, rp += stride) {
+            const unsigned long long e = *rp;
+            if (r < cnt && (uint32_t)(e >> 32) <= kth) { *wp = e; wp += stride; w++; }
         }
-        // surplus ties at the k-th distance (rare): drop the largest original index until k remain
         ICP_ASSERT(w <= CAP && w <= cnt);
-        while (w > k) {
-            int worst = 0;
-            unsigned long long worst_key = 0ull;
-            for (int r = 0; r < w; r++) {
-                const unsigned long long e = buf[r * stride];
-                const unsigned long long key = (e & 0xffffffff00000000ull) | __float_as_uint(ldg4(pts + (uint32_t)e).w);
-                if (key >= worst_key) { worst_key = key; worst = r; }
-            }
-            w--;
-            buf[worst * stride] = buf[w * stride];
-        }
+        // surplus ties at the k-th distance (rare): drop the largest original index until k remain
+        if (w > k) w = knn_drop_ties(buf, stride, w, k, pts);
         cnt = done = w;
     }
     // merge and prune when some lane has no room left for another leaf group
@@ -509,12 +585,14 @@ __device__ __forceinline__ void knn_offer_leaf(KList<KMAX, EXACT>& L, const floa
     const float4* lp = pts + (size_t)g * ICP_LEAF;
     const NegQuery nq = make_neg_query(qx, qy, qz);
 #pragma unroll
-    for (int j = 0; j < ICP_LEAF; j++) {
-        const float4 c = ldg4(lp + j);
-        const float dd = dist2_packed(nq, c);
-        db[j] = (__float_as_uint(c.w) != (uint32_t)ICP_INVALID_ID) ? __float_as_uint(dd) : 0xffffffffu;
-    }
-    const uint32_t thr = take ? L.kth : 0u;
+    for (int j = 0; j < ICP_LEAF; j++) db[j] = __float_as_uint(dist2_packed(nq, ldg4(lp + j)));
+    // padding points sit at (FLT_MAX, FLT_MAX, FLT_MAX): their squared distance is +inf, above the cap, so they are
+    // never parked -- not even while the list is unfilled (kth = ICP_KNN_UNFILLED)
+#ifdef ICP_KNN_CHECK_ID
+#pragma unroll
+    for (int j = 0; j < ICP_LEAF; j++) if (__float_as_uint(ldg4(lp + j).w) == (uint32_t)ICP_INVALID_ID) db[j] = 0xffffffffu;
+#endif
+    const uint32_t thr = take ? bound_cap(L.kth) : 0u;
 #pragma unroll
     for (int j = 0; j < ICP_LEAF; j++) {
         if (db[j] <= thr && take) {
@@ -531,6 +609,7 @@ template <int KMAX, bool EXACT>
 struct KnnVisitor {
     static constexpr bool kTrackMargin = false;
     static constexpr bool kBudget = false;
+    static constexpr bool kBoundCache = false;   // the normals kernel has no shared memory to spare
     __device__ __forceinline__ bool exhausted() const { return false; }
     __device__ __forceinline__ void prune(uint32_t) {}
     KList<KMAX, EXACT>& L;
@@ -539,6 +618,7 @@ struct KnnVisitor {
     int k;
     uint32_t g_lo, g_hi;
     bool active;
+    uint32_t* lbc;   // unused (kBoundCache = false)
     __device__ __forceinline__ uint32_t bound_bits() const { return L.bound_bits(); }
     __device__ __forceinline__ void set_active(bool a) { active = a; }   // a bystander must not park candidates
     __device__ __forceinline__ bool leaf(uint32_t g, bool act) {
@@ -556,7 +636,7 @@ __device__ __forceinline__ void knn_traverse_warp(const TreeShape& sh, const Wid
                                                   const float4* __restrict__ seg_pts, float qx, float qy, float qz,
                                                   int k, uint32_t g_lo, uint32_t g_hi, bool active, uint32_t split_mask,
                                                   KList<KMAX, EXACT>& L) {
-    KnnVisitor<KMAX, EXACT> v{L, seg_pts, qx, qy, qz, k, g_lo, g_hi, active};
+    KnnVisitor<KMAX, EXACT> v{L, seg_pts, qx, qy, qz, k, g_lo, g_hi, active, nullptr};
     L.flush(k);                                   // the caller's window scan
     wide_traverse_warp(sh, seg_nodes, qx, qy, qz, active, split_mask, v);
     L.flush(k);

@@ -49,14 +49,17 @@ def child(lib, n):
         h2 = hashlib.md5(np.ascontiguousarray(Tm).tobytes()).hexdigest()[:8]
         per = ""
         ctx.set_option(icp.OPT_KERNEL_TIMING, 1)
-        best = None
-        for _ in range(4):
+        runs = []
+        for _ in range(int(os.environ.get("REPS", "10"))):
             with torch.cuda.stream(stream):
                 flush.zero_()
             ctx.register_symm(50, 1.0)
             cur, sol = ctx.search_times()
-            best = cur if best is None else np.minimum(best, cur)
-        per = " searches[" + " ".join(f"{x:.3f}" for x in best) + f"] solve {float(sol.mean())*1e3:.1f}us"
+            runs.append(cur)
+        runs = np.array(runs)
+        best, med = runs.min(axis=0), np.median(runs, axis=0)
+        per = (" searches[" + " ".join(f"{x:.3f}" for x in best) + "] med[" + " ".join(f"{x:.3f}" for x in med)
+               + f"] sum {best.sum():.3f}/{med.sum():.3f} solve {float(sol.mean())*1e3:.1f}us")
         ms = sorted(ms[2:])
         print(f"{os.path.basename(lib):28s} loop best {ms[0]:.3f} med {ms[len(ms)//2]:.3f} iters {st['iters']}{per} normals(both) {min(tn)*1e3:.3f} corr {h1} T {h2} nrm {h3}",
               flush=True)
