@@ -17,6 +17,16 @@
 
 namespace {
 
+// slot j of the pitched layout -> (segment, position).  Almost every cloud set has fewer than 2^32 slots, and a
+// 64-bit division costs a hundred instructions per thread in kernels that otherwise do a handful of loads.
+__device__ __forceinline__ void split_slot(size_t j, uint32_t pitch, uint32_t& seg, uint32_t& i) {
+    if (j <= 0xffffffffull) {
+        const uint32_t j32 = (uint32_t)j;
+        seg = j32 / pitch; i = j32 - seg * pitch;
+    } else {
+        seg = (uint32_t)(j / pitch); i = (uint32_t)(j - (size_t)seg * pitch);
+    }
+}
 
 __global__ void bbox_init_kernel(uint32_t* bbox, uint32_t nseg, int* flags) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -49,13 +59,29 @@ __global__ void __launch_bounds__(256) bbox_kernel(const char* __restrict__ raw,
         hi[d] = __reduce_max_sync(0xffffffffu, hi[d]);
     }
     bad = __any_sync(0xffffffffu, bad);
-    if ((threadIdx.x & 31) == 0) {
+    // one set of global atomics per BLOCK: all blocks of a segment hit the same six words, and with one set per warp
+    // the kernel spent most of its time queueing at them
+    __shared__ uint32_t s_lo[8][3], s_hi[8][3];
+    __shared__ int s_bad[8];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) {
 #pragma unroll
-        for (int d = 0; d < 3; d++) {
-            atomicMin(&bbox[seg * 8 + d], lo[d]);
-            atomicMax(&bbox[seg * 8 + 4 + d], hi[d]);
-        }
-        if (bad) atomicAdd(flags, 1);
+        for (int d = 0; d < 3; d++) { s_lo[warp][d] = lo[d]; s_hi[warp][d] = hi[d]; }
+        s_bad[warp] = bad;
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        uint32_t l = 0xffffffffu, h = 0u;
+#pragma unroll
+        for (int w = 0; w < 8; w++) { l = min(l, s_lo[w][threadIdx.x]); h = max(h, s_hi[w][threadIdx.x]); }
+        atomicMin(&bbox[seg * 8 + threadIdx.x], l);
+        atomicMax(&bbox[seg * 8 + 4 + threadIdx.x], h);
+    }
+    if (threadIdx.x == 3) {
+        int b = 0;
+#pragma unroll
+        for (int w = 0; w < 8; w++) b |= s_bad[w];
+        if (b) atomicAdd(flags, 1);
     }
 }
 
@@ -89,32 +115,36 @@ __device__ __forceinline__ uint32_t spread10(uint32_t v) {  // 10 bits -> every 
 // per query).
 __device__ __forceinline__ uint32_t hilbert_index(uint32_t x, uint32_t y, uint32_t z, int bits) {
     uint32_t X[3] = {x, y, z};
+    // branch-free (the two cases of every step differ per thread: as branches they serialise the warp)
     for (uint32_t Q = 1u << (bits - 1); Q > 1u; Q >>= 1) {
         const uint32_t Pm = Q - 1u;
 #pragma unroll
         for (int i = 0; i < 3; i++) {
-            if (X[i] & Q) X[0] ^= Pm;
-            else { uint32_t t = (X[0] ^ X[i]) & Pm; X[0] ^= t; X[i] ^= t; }
+            const uint32_t set = (X[i] & Q) ? 0xffffffffu : 0u;          // bit set: invert the low bits of X[0]
+            const uint32_t t = (X[0] ^ X[i]) & Pm & ~set;                // bit clear: exchange the low bits of X[0] and X[i]
+            X[0] ^= (Pm & set) | t;
+            X[i] ^= t;
         }
     }
     X[1] ^= X[0];
     X[2] ^= X[1];
     uint32_t t = 0;
-    for (uint32_t Q = 1u << (bits - 1); Q > 1u; Q >>= 1)
-        if (X[2] & Q) t ^= Q - 1u;
+    for (uint32_t Q = 1u << (bits - 1); Q > 1u; Q >>= 1) t ^= (X[2] & Q) ? Q - 1u : 0u;
     X[0] ^= t; X[1] ^= t; X[2] ^= t;
     return (spread10(X[0]) << 2) | (spread10(X[1]) << 1) | spread10(X[2]);
 }
 
 // one thread per slot of the pitched layout
+template <typename KeyT>   // 32-bit keys when segment bits + curve bits fit (every single pair): the sort moves a third less
 __global__ void __launch_bounds__(256) curve_key_kernel(const char* __restrict__ raw, size_t stride_bytes,
                                                      const uint32_t* __restrict__ counts, uint32_t max_count,
                                                      uint32_t pitch, uint32_t nseg, const float4* __restrict__ bb_lo,
                                                      const float4* __restrict__ bb_hi, int bits,
-                                                     unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals) {
+                                                     KeyT* __restrict__ keys, uint32_t* __restrict__ vals) {
     size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= (size_t)nseg * pitch) return;
-    uint32_t seg = (uint32_t)(j / pitch), i = (uint32_t)(j - (size_t)seg * pitch);
+    uint32_t seg, i;
+    split_slot(j, pitch, seg, i);
     // padding takes the largest index: the sort is stable and padding slots follow the real ones in the
     // input, so they still end up last in their segment
     const uint32_t cells = 1u << bits;
@@ -129,7 +159,7 @@ __global__ void __launch_bounds__(256) curve_key_kernel(const char* __restrict__
         uint32_t cz = min(cells - 1u, (uint32_t)((p[2] - lo.z) * scale));
         code = hilbert_index(cx, cy, cz, bits);
     }
-    keys[j] = ((unsigned long long)seg << (3 * bits)) | code;
+    keys[j] = (KeyT)(((unsigned long long)seg << (3 * bits)) | code);
     vals[j] = i;
 }
 
@@ -139,7 +169,8 @@ __global__ void __launch_bounds__(256) gather_kernel(const char* __restrict__ ra
                                                      float4* __restrict__ pts) {
     size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= (size_t)nseg * pitch) return;
-    uint32_t seg = (uint32_t)(j / pitch);
+    uint32_t seg, i_unused;
+    split_slot(j, pitch, seg, i_unused);
     uint32_t v = vals[j];
     if (v < counts[seg]) {
         const float* p = reinterpret_cast<const float*>(raw + ((size_t)seg * max_count + v) * stride_bytes);
@@ -154,7 +185,8 @@ __global__ void __launch_bounds__(256) init_nodes_kernel(WideNode* __restrict__ 
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_floats) return;
     const float inf = __int_as_float(0x7f800000);
-    reinterpret_cast<float*>(nodes)[t] = ((t % 48) < 24) ? inf : -inf;
+    const uint32_t r = t <= 0xffffffffull ? (uint32_t)t % 48u : (uint32_t)(t % 48);
+    reinterpret_cast<float*>(nodes)[t] = (r < 24) ? inf : -inf;
 }
 
 // ---- local k-d refinement of the curve order ----------------------------------------------
@@ -596,7 +628,8 @@ __global__ void __launch_bounds__(256) upper_box_kernel(WideNode* __restrict__ n
                                                         uint32_t level_off, uint32_t level_cnt, uint32_t parent_off) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (size_t)nseg * level_cnt) return;
-    uint32_t seg = (uint32_t)(t / level_cnt), i = (uint32_t)(t - (size_t)seg * level_cnt);
+    uint32_t seg, i;
+    split_slot(t, level_cnt, seg, i);
     WideNode* base = nodes + (size_t)seg * sh.nodes_per_seg;
     const WideNode* me = base + level_off + i;
     const float inf = __int_as_float(0x7f800000);
@@ -618,7 +651,8 @@ __global__ void __launch_bounds__(256) finish_units_kernel(const float4* __restr
     const size_t wid = ((size_t)blockIdx.x * 256 + threadIdx.x) >> 5;
     const uint32_t lane = threadIdx.x & 31;
     if (wid >= (size_t)nseg * sh.units_per_seg) return;
-    const uint32_t seg = (uint32_t)(wid / sh.units_per_seg), unit = (uint32_t)(wid - (size_t)seg * sh.units_per_seg);
+    uint32_t seg, unit;
+    split_slot(wid, sh.units_per_seg, seg, unit);
     const uint32_t i = unit * 32u + lane;
     const bool in_pitch = i < sh.pitch;
     float4 p = make_float4(0.f, 0.f, 0.f, __uint_as_float((uint32_t)ICP_INVALID_ID));
@@ -854,21 +888,32 @@ int icp_build_cloudset(icpsymm_ctx* ctx, CloudSet& cs, const float* xyz, bool on
 #else
     const int curve_bits = 10;
 #endif
-    curve_key_kernel<<<gb, 256, 0, st>>>(raw, stride_bytes, cs.counts, mc, sh.pitch, ns, cs.bb_lo, cs.bb_hi, curve_bits,
-                                      B.keys_a, B.vals_a);
     int seg_bits = 0;
     while ((1ull << seg_bits) < nseg) seg_bits++;
-    int end_bit = 3 * curve_bits + seg_bits;
+    const int end_bit = 3 * curve_bits + seg_bits;
     size_t temp_bytes = 0;
-    ICP_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, B.keys_a, B.keys_b, B.vals_a,
-                                                   B.vals_b, slots, 0, end_bit, st));
-    {
+    if (end_bit <= 32 && slots < 0x7fffffffull) {
+        // 32-bit keys and 32-bit offsets (the key buffers are reused as they are)
+        uint32_t* ka = reinterpret_cast<uint32_t*>(B.keys_a);
+        uint32_t* kb = reinterpret_cast<uint32_t*>(B.keys_b);
+        curve_key_kernel<uint32_t><<<gb, 256, 0, st>>>(raw, stride_bytes, cs.counts, mc, sh.pitch, ns, cs.bb_lo, cs.bb_hi,
+                                                       curve_bits, ka, B.vals_a);
+        ICP_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, ka, kb, B.vals_a, B.vals_b, (int)slots, 0, end_bit, st));
         char* tmp = (char*)B.cub_temp;
         if ((rc = icp_reserve(ctx, &tmp, &B.cub_temp_bytes, temp_bytes))) return rc;
         B.cub_temp = tmp;
+        ICP_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(B.cub_temp, temp_bytes, ka, kb, B.vals_a, B.vals_b, (int)slots, 0, end_bit, st));
+    } else {
+        curve_key_kernel<unsigned long long><<<gb, 256, 0, st>>>(raw, stride_bytes, cs.counts, mc, sh.pitch, ns, cs.bb_lo,
+                                                                 cs.bb_hi, curve_bits, B.keys_a, B.vals_a);
+        ICP_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, B.keys_a, B.keys_b, B.vals_a,
+                                                       B.vals_b, slots, 0, end_bit, st));
+        char* tmp = (char*)B.cub_temp;
+        if ((rc = icp_reserve(ctx, &tmp, &B.cub_temp_bytes, temp_bytes))) return rc;
+        B.cub_temp = tmp;
+        ICP_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(B.cub_temp, temp_bytes, B.keys_a, B.keys_b, B.vals_a,
+                                                       B.vals_b, slots, 0, end_bit, st));
     }
-    ICP_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(B.cub_temp, temp_bytes, B.keys_a, B.keys_b, B.vals_a,
-                                                   B.vals_b, slots, 0, end_bit, st));
     gather_kernel<<<gb, 256, 0, st>>>(raw, stride_bytes, cs.counts, mc, sh.pitch, ns, B.vals_b, cs.pts);
     {
         // k-d refinement of the curve order: coarse median partitions of 8192-point windows (the set that is
