@@ -35,9 +35,6 @@
 #ifndef ICP_WIDE_NODE
 #define ICP_WIDE_NODE 1
 #endif
-#ifndef ICP_BOUND_CACHE
-#define ICP_BOUND_CACHE 0   // re-test stale leaf groups from a shared-memory cache of the lanes' bounds (search.cuh): measured, no gain
-#endif
 #include "search.cuh"
 
 #ifdef ICP_BLOCK_TIMES   // developer instrumentation: per-block start/end/SM of the last K1 launch
@@ -316,15 +313,7 @@ __global__ void __launch_bounds__(kNNThreads, kNNBlocksPerSM) nn_accum_kernel(co
     __shared__ int sTrack;            // walks of this search record margins (K2 expects the next step to be small)
     __shared__ int sProbe;            // the probe kernel has left one seed per tile
     __shared__ uint32_t sWork[2];
-#if ICP_BOUND_CACHE
-    __shared__ uint32_t sBoundCache[ICP_FAN * kNNThreads];   // [warp][child][lane], see warp_node_test
-#endif
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-#if ICP_BOUND_CACHE
-    uint32_t* const lbc = sBoundCache + warp * (ICP_FAN * 32) + lane;
-#else
-    uint32_t* const lbc = nullptr;
-#endif
     const LoopParams lp = *P.lp;
     uint32_t cur_seg = 0xffffffffu;
     // tickets 0 .. gridDim-1 are implicit (the counter starts at gridDim); the ticket of the NEXT tile is drawn
@@ -439,11 +428,11 @@ __global__ void __launch_bounds__(kNNThreads, kNNBlocksPerSM) nn_accum_kernel(co
         if (!lp.identity_pairs && nt > 0 && __any_sync(0xffffffffu, walk)) {
             uint8_t* ref_slot = P.ref_search + (size_t)seg * P.src.shape.pitch + i;
             if (sTrack && may_skip && sSearch < 0xffu) {
-                const WalkResult r = nn_walk<true>(&P.tgt.shape, tbox, tpts, p.x, p.y, p.z, walk, b.key, lbc);
+                const WalkResult r = nn_walk<true>(&P.tgt.shape, tbox, tpts, p.x, p.y, p.z, walk, b.key);
                 b.key = r.key;
                 if (walk) { P.margin2[(size_t)seg * P.src.shape.pitch + i] = __uint_as_float(r.m2); *ref_slot = (uint8_t)sSearch; }
             } else {
-                const WalkResult r = nn_walk<false>(&P.tgt.shape, tbox, tpts, p.x, p.y, p.z, walk, b.key, lbc);
+                const WalkResult r = nn_walk<false>(&P.tgt.shape, tbox, tpts, p.x, p.y, p.z, walk, b.key);
                 b.key = r.key;
                 if (walk && may_skip) *ref_slot = 0xffu;   // walked without tracking: the old margin belongs to another winner
             }

@@ -104,24 +104,11 @@ __global__ void __launch_bounds__(128, (KMAX <= 16) ? ICP_NRM_BLOCKS : 4) normal
         const uint32_t w_lo = __reduce_min_sync(0xffffffffu, active ? g_lo : 0xffffffffu);
         const uint32_t w_hi = __reduce_max_sync(0xffffffffu, active ? g_hi : 0u);
         if (w_lo != 0xffffffffu) {
-#ifdef ICP_NRM_OWN_FIRST
-            // start with the warp's own 32-point unit and wrap around the cell: its points are the nearest of the cell,
-            // so the first merge already leaves a tight k-th distance and the rest of the cell parks few candidates
-            const uint32_t start = (i & ~31u) / ICP_LEAF - w_lo;
-#pragma unroll 1
-            for (uint32_t t = 0; t < w; t++) {
-                const uint32_t gg = w_lo + ((t + start) & (w - 1u));
-                if (gg > w_hi) continue;
-                knn_offer_leaf(L, pts, gg, q.x, q.y, q.z, active && gg >= g_lo && gg <= g_hi);
-                L.maybe_flush(k, pts);
-            }
-#else
 #pragma unroll 1
             for (uint32_t gg = w_lo; gg <= w_hi; gg++) {
                 knn_offer_leaf(L, pts, gg, q.x, q.y, q.z, active && gg >= g_lo && gg <= g_hi);
                 L.maybe_flush(k, pts);
             }
-#endif
         }
     }
     // warp-uniform: blocks start at multiples of 128 points, so a warp is exactly one 32-point unit

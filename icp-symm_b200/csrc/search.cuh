@@ -213,13 +213,7 @@ template <typename V>
 __device__ __forceinline__ uint32_t warp_node_test(const WideNode* __restrict__ nd, float qx, float qy, float qz,
                                                    uint32_t my_bound, bool active, const WarpPatch& pb,
                                                    uint32_t max_bound, bool far_mode, int& pref, V& v,
-                                                   bool children_are_leaves, bool& cached) {
-    // BOUND CACHE (V::kBoundCache).  A lane's lower bound of a child box depends on the query and the box only, not on
-    // the lane's current bound.  When the children are leaf groups the warp stays at this node until all of them are
-    // popped, so the bounds computed here are parked in a per-lane shared-memory column (v.lbc[c * 32]) and a stale
-    // child is re-tested by ONE shared load instead of six global loads and the box arithmetic.  `cached` tells
-    // whether every admitted child has its entry (the patch-only shortcut computes no per-lane bounds).
-    cached = false;
+                                                   bool children_are_leaves = true) {
     // A walk with only a few live lanes (the lanes of a unit that could not keep their winners, K1 skip test) is "far"
     // by the patch criterion -- its patch is tiny -- but 32 exact tests per child are wasted on it: above the leaf
     // parents the patch test alone selects nearly the same children (a superset; the extra ones are cut one level
@@ -232,11 +226,6 @@ __device__ __forceinline__ uint32_t warp_node_test(const WideNode* __restrict__ 
         const uint32_t mine = dense_children_test(nd, qx, qy, qz, my_bound, kmin, bb);
         pref = (int)(__reduce_min_sync(0xffffffffu, active ? kmin : 0xffffffffu) & 7u);
         const uint32_t mask = __reduce_or_sync(0xffffffffu, active ? mine : 0u);
-        if (V::kBoundCache && children_are_leaves) {
-#pragma unroll
-            for (int c = 0; c < ICP_FAN; c++) v.lbc[c * 32] = bb[c];
-            cached = true;
-        }
         if (V::kTrackMargin) {
 #pragma unroll
             for (int c = 0; c < ICP_FAN; c++) v.prune(((mask >> c) & 1u) ? 0xffffffffu : bb[c]);
@@ -267,11 +256,6 @@ __device__ __forceinline__ uint32_t warp_node_test(const WideNode* __restrict__ 
         uint32_t kmin, bb[ICP_FAN];
         const uint32_t mine = dense_children_test(nd, qx, qy, qz, my_bound, kmin, bb);
         mask2 = __reduce_or_sync(0xffffffffu, active ? mine : 0u) & mask1;
-        if (V::kBoundCache && children_are_leaves) {
-#pragma unroll
-            for (int c = 0; c < ICP_FAN; c++) v.lbc[c * 32] = bb[c];
-            cached = true;
-        }
         if (V::kTrackMargin) {
 #pragma unroll
             for (int c = 0; c < ICP_FAN; c++) v.prune(((mask2 >> c) & 1u) ? 0xffffffffu : bb[c]);
@@ -285,12 +269,9 @@ __device__ __forceinline__ uint32_t warp_node_test(const WideNode* __restrict__ 
             const float lz = __shfl_sync(0xffffffffu, blz, c), hx = __shfl_sync(0xffffffffu, bhx, c);
             const float hy = __shfl_sync(0xffffffffu, bhy, c), hz = __shfl_sync(0xffffffffu, bhz, c);
             const uint32_t lb = point_box_bits(lx, ly, lz, hx, hy, hz, qx, qy, qz);
-            if (__any_sync(0xffffffffu, active && lb <= my_bound && lb != ICP_INF_BITS)) {
-                mask2 |= 1u << c;
-                if (V::kBoundCache && children_are_leaves) v.lbc[c * 32] = lb;
-            } else if (V::kTrackMargin) v.prune(lb);
+            if (__any_sync(0xffffffffu, active && lb <= my_bound && lb != ICP_INF_BITS)) mask2 |= 1u << c;
+            else if (V::kTrackMargin) v.prune(lb);
         }
-        cached = V::kBoundCache && children_are_leaves;
     }
     return mask2;
 }
@@ -303,15 +284,6 @@ __device__ __forceinline__ bool warp_child_recheck(const WideNode* __restrict__ 
     const uint32_t lb = point_box_bits(__ldg(f), __ldg(f + 8), __ldg(f + 16), __ldg(f + 24), __ldg(f + 32),
                                        __ldg(f + 40), qx, qy, qz);
     const bool enter = __any_sync(0xffffffffu, active && lb <= my_bound && lb != ICP_INF_BITS);
-    if (V::kTrackMargin && !enter) v.prune(lb);
-    return enter;
-}
-
-// the same re-test from the bound cache (see warp_node_test)
-template <typename V>
-__device__ __forceinline__ bool warp_child_recheck_cached(int c, uint32_t my_bound, bool active, V& v) {
-    const uint32_t lb = v.lbc[c * 32];
-    const bool enter = __any_sync(0xffffffffu, active && lb <= bound_cap(my_bound));
     if (V::kTrackMargin && !enter) v.prune(lb);
     return enter;
 }
@@ -342,8 +314,7 @@ __device__ __forceinline__ void wide_traverse_group(const TreeShape& sh, const W
     uint32_t stale = 0;   // bit l: the pending mask of level l predates the latest bound improvement
     int l = top, pref;
     uint32_t i = 0;
-    bool cached;   // the bound cache covers the pending children of the current level-1 node
-    uint32_t cur = warp_node_test(rec, qx, qy, qz, v.bound_bits(), active, pb, max_bound, far_mode, pref, v, top == 1, cached);
+    uint32_t cur = warp_node_test(rec, qx, qy, qz, v.bound_bits(), active, pb, max_bound, far_mode, pref, v, top == 1);
     unsigned long long saved = 0ull;   // byte l-1: pending mask of the open ancestor at level l
     for (;;) {
         if (V::kBudget && v.exhausted()) break;
@@ -359,11 +330,7 @@ __device__ __forceinline__ void wide_traverse_group(const TreeShape& sh, const W
         const int c = (pref >= 0 && ((cur >> pref) & 1u)) ? pref : (__ffs((int)cur) - 1);
         pref = -1;
         cur &= ~(1u << c);
-        if ((stale >> l) & 1u) {
-            const bool enter = (V::kBoundCache && l == 1 && cached) ? warp_child_recheck_cached(c, v.bound_bits(), active, v)
-                                                                    : warp_child_recheck(rec, c, qx, qy, qz, v.bound_bits(), active, v);
-            if (!enter) continue;
-        }
+        if (((stale >> l) & 1u) && !warp_child_recheck(rec, c, qx, qy, qz, v.bound_bits(), active, v)) continue;
         const uint32_t child = (i << ICP_LOG_FAN) + (uint32_t)c;
         ICP_ASSERT(l >= 1 && l <= top && i < sh.level_cnt[l] && child < sh.level_cnt[l - 1]);
         bool improved = false;
@@ -375,7 +342,7 @@ __device__ __forceinline__ void wide_traverse_group(const TreeShape& sh, const W
             saved = (saved & ~(0xffull << sh8)) | ((unsigned long long)cur << sh8);
             --l; i = child;
             rec = seg_nodes + sh.level_off[l] + i;
-            cur = warp_node_test(rec, qx, qy, qz, v.bound_bits(), active, pb, max_bound, far_mode, pref, v, l == 1, cached);
+            cur = warp_node_test(rec, qx, qy, qz, v.bound_bits(), active, pb, max_bound, far_mode, pref, v, l == 1);
             stale &= ~(1u << l);
         }
         if (improved) {   // some active lane's bound improved (warp-uniform)
@@ -408,11 +375,10 @@ __device__ __forceinline__ void wide_traverse_warp(const TreeShape& sh, const Wi
 // pinned fp32 arithmetic (a box bound never exceeds the fp32 distance of a member point).  K1 stores it and uses it
 // in later searches: while the query has moved by less than the gap between the winner's distance and the margin,
 // the winner cannot have changed and the walk is skipped (icp_loop.cu).
-template <bool TRACK, bool BUDGET = false, bool CACHE = false>
+template <bool TRACK, bool BUDGET = false>
 struct NNVisitor {
     static constexpr bool kTrackMargin = TRACK;
     static constexpr bool kBudget = BUDGET;   // the walk may stop early (probe: any real point is a useful seed)
-    static constexpr bool kBoundCache = CACHE;
     int budget = 0;                           // leaf scans left
     __device__ __forceinline__ bool exhausted() const { return BUDGET && budget <= 0; }
     Best& b;
@@ -420,7 +386,6 @@ struct NNVisitor {
     float qx, qy, qz;
     NegQuery nq;
     uint32_t m2;
-    uint32_t* lbc;                            // this lane's column of the bound cache (shared memory, stride 32), or null
     __device__ __forceinline__ uint32_t bound_bits() const { return (uint32_t)(b.key >> 32); }
     __device__ __forceinline__ void set_active(bool) {}
     __device__ __forceinline__ void prune(uint32_t lower_bound_bits) { if (TRACK) m2 = min(m2, lower_bound_bits); }
@@ -436,21 +401,17 @@ struct NNVisitor {
 // Out-of-line entry of the walk: its own register allocation, so that the margin-tracking flavour (more live
 // state) does not tax the lean one when a kernel holds both.
 struct WalkResult { unsigned long long key; uint32_t m2; };
-#ifndef ICP_BOUND_CACHE
-#define ICP_BOUND_CACHE 0   // a translation unit whose walks get a shared-memory column per lane defines it to 1
-#endif
 template <bool TRACK>
 __device__ __forceinline__ uint32_t nn_traverse_warp(const TreeShape& sh, const WideNode* __restrict__ seg_nodes,
                                                      const float4* __restrict__ seg_pts, float qx, float qy, float qz,
-                                                     bool active, uint32_t split_mask, Best& b, uint32_t* lbc = nullptr);
-// lbc: this lane's column of the bound cache (8 words, stride 32, shared memory); used when ICP_BOUND_CACHE
+                                                     bool active, uint32_t split_mask, Best& b);
 template <bool TRACK>
 __device__ __noinline__ WalkResult nn_walk(const TreeShape* sh, const WideNode* __restrict__ seg_nodes,
                                            const float4* __restrict__ seg_pts, float qx, float qy, float qz, bool active,
-                                           unsigned long long key, uint32_t* lbc) {
+                                           unsigned long long key) {
     Best b; b.key = key;
     WalkResult r;
-    r.m2 = nn_traverse_warp<TRACK>(*sh, seg_nodes, seg_pts, qx, qy, qz, active, 0u, b, lbc);
+    r.m2 = nn_traverse_warp<TRACK>(*sh, seg_nodes, seg_pts, qx, qy, qz, active, 0u, b);
     r.key = b.key;
     return r;
 }
@@ -459,8 +420,8 @@ __device__ __noinline__ WalkResult nn_walk(const TreeShape* sh, const WideNode* 
 template <bool TRACK>
 __device__ __forceinline__ uint32_t nn_traverse_warp(const TreeShape& sh, const WideNode* __restrict__ seg_nodes,
                                                      const float4* __restrict__ seg_pts, float qx, float qy, float qz,
-                                                     bool active, uint32_t split_mask, Best& b, uint32_t* lbc) {
-    NNVisitor<TRACK, false, ICP_BOUND_CACHE != 0> v{0, b, seg_pts, qx, qy, qz, make_neg_query(qx, qy, qz), TRACK ? ICP_INF_BITS : 0u, lbc};
+                                                     bool active, uint32_t split_mask, Best& b) {
+    NNVisitor<TRACK> v{0, b, seg_pts, qx, qy, qz, make_neg_query(qx, qy, qz), TRACK ? ICP_INF_BITS : 0u};
     wide_traverse_warp(sh, seg_nodes, qx, qy, qz, active, split_mask, v);
     return v.m2;
 }
@@ -471,7 +432,7 @@ static __device__ __noinline__ unsigned long long nn_walk_budget(const TreeShape
                                                           const float4* __restrict__ seg_pts, float qx, float qy, float qz,
                                                           bool active, unsigned long long key, int budget) {
     Best b; b.key = key;
-    NNVisitor<false, true> v{budget, b, seg_pts, qx, qy, qz, make_neg_query(qx, qy, qz), 0u, nullptr};
+    NNVisitor<false, true> v{budget, b, seg_pts, qx, qy, qz, make_neg_query(qx, qy, qz), 0u};
     wide_traverse_warp(*sh, seg_nodes, qx, qy, qz, active, 0u, v);
     return b.key;
 }
@@ -609,7 +570,6 @@ template <int KMAX, bool EXACT>
 struct KnnVisitor {
     static constexpr bool kTrackMargin = false;
     static constexpr bool kBudget = false;
-    static constexpr bool kBoundCache = false;   // the normals kernel has no shared memory to spare
     __device__ __forceinline__ bool exhausted() const { return false; }
     __device__ __forceinline__ void prune(uint32_t) {}
     KList<KMAX, EXACT>& L;
@@ -618,7 +578,6 @@ struct KnnVisitor {
     int k;
     uint32_t g_lo, g_hi;
     bool active;
-    uint32_t* lbc;   // unused (kBoundCache = false)
     __device__ __forceinline__ uint32_t bound_bits() const { return L.bound_bits(); }
     __device__ __forceinline__ void set_active(bool a) { active = a; }   // a bystander must not park candidates
     __device__ __forceinline__ bool leaf(uint32_t g, bool act) {
@@ -636,7 +595,7 @@ __device__ __forceinline__ void knn_traverse_warp(const TreeShape& sh, const Wid
                                                   const float4* __restrict__ seg_pts, float qx, float qy, float qz,
                                                   int k, uint32_t g_lo, uint32_t g_hi, bool active, uint32_t split_mask,
                                                   KList<KMAX, EXACT>& L) {
-    KnnVisitor<KMAX, EXACT> v{L, seg_pts, qx, qy, qz, k, g_lo, g_hi, active, nullptr};
+    KnnVisitor<KMAX, EXACT> v{L, seg_pts, qx, qy, qz, k, g_lo, g_hi, active};
     L.flush(k);                                   // the caller's window scan
     wide_traverse_warp(sh, seg_nodes, qx, qy, qz, active, split_mask, v);
     L.flush(k);
