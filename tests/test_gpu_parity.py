@@ -533,6 +533,16 @@ def test_result_does_not_depend_on_the_batch_a_pair_sits_in(ctx):
         assert np.array_equal(Tb[b], res[b][0]), b
         assert stb[b]["iters"] == res[b][1]["iters"] and stb[b]["diff"] == res[b][1]["diff"]
         assert np.array_equal(idxb[b, :counts[b]], res[b][2])
+    # the same pairs twice in one batch of six: more than four segments take the 64-bit sort keys of the index
+    # build (segment bits + 30 curve bits no longer fit 32), single pairs and small batches the 32-bit ones
+    S6, T6, c6 = np.concatenate([S, S]), np.concatenate([Tg, Tg]), np.concatenate([counts, counts])
+    ctx.set_source_batch(S6, c6); ctx.set_target_batch(T6, c6); ctx.estimate_normals(10)
+    T6b, st6, _ = ctx.register_symm(30, 1e-3)
+    idx6 = ctx.get_correspondences()[0].reshape(6, m)
+    for b in range(6):
+        assert np.array_equal(T6b[b], res[b % 3][0]), b
+        assert st6[b]["iters"] == res[b % 3][1]["iters"] and st6[b]["diff"] == res[b % 3][1]["diff"]
+        assert np.array_equal(idx6[b, :c6[b]], res[b % 3][2])
 
 
 def test_register_npoint_regist_h(ctx, cat, cat_out, gold):
