@@ -90,6 +90,7 @@ void icpsymm_destroy(icpsymm_ctx* ctx) {
     for (int k = 0; k < 2; k++) {
         if (ctx->aux[k]) { cudaStreamSynchronize(ctx->aux[k]); cudaStreamDestroy(ctx->aux[k]); }
         if (ctx->ready[k]) cudaEventDestroy(ctx->ready[k]);
+        if (ctx->built[k]) cudaEventDestroy(ctx->built[k]);
         BuildScratch& B = ctx->scratch[k];
         cudaFree(B.staging); cudaFree(B.keys_a); cudaFree(B.keys_b); cudaFree(B.vals_a); cudaFree(B.vals_b);
         cudaFree(B.cub_temp); cudaFree(B.d_flags);

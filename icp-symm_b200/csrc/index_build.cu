@@ -751,6 +751,7 @@ cudaStream_t icp_cloud_stream(icpsymm_ctx* ctx, CloudSet& cs) {
     if (!ctx->aux[k]) {
         if (cudaStreamCreateWithFlags(&ctx->aux[k], cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); return ctx->stream; }
         cudaEventCreateWithFlags(&ctx->ready[k], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&ctx->built[k], cudaEventDisableTiming);
     }
     if (!ctx->fork_ev) cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming);
     // order after everything already enqueued on the context stream (it may still read this cloud)
@@ -775,7 +776,9 @@ int icp_join_clouds(icpsymm_ctx* ctx, bool check) {
         }
         if (check && cs->pending_check) {
             cs->pending_check = false;
-            cudaEventSynchronize(ctx->ready[cs->slot]);
+            // wait for the BUILD only: the normals that may follow it on the same stream keep running while the host
+            // enqueues the loop (waiting for `ready` made the host idle through the normals of every pipelined pair)
+            cudaEventSynchronize(ctx->built[cs->slot]);
             if (ctx->scratch[cs->slot].h_flag && *ctx->scratch[cs->slot].h_flag) {
                 cs->valid = false;
                 rc = icp_fail_msg(ctx, ICPSYMM_ERR_NONFINITE, "cloud holds NaN/Inf coordinates");
@@ -961,6 +964,7 @@ int icp_build_cloudset(icpsymm_ctx* ctx, CloudSet& cs, const float* xyz, bool on
     if (ctx->opt_async_setup && st != ctx->stream) {
         // asynchronous setup: no host wait here; the flag is read at the next point that hands data
         // to the host (icp_join_clouds), so the upload of the other cloud overlaps this build
+        ICP_CUDA_CHECK(cudaEventRecord(ctx->built[cs.slot], st));
         icp_cloud_done(ctx, cs);
         cs.pending_check = true;
     } else {

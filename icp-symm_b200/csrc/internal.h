@@ -76,7 +76,8 @@ struct icpsymm_ctx {
     // build scratch (grow-only) and the aux streams of the asynchronous setup
     BuildScratch scratch[2];
     cudaStream_t aux[2] = {nullptr, nullptr};
-    cudaEvent_t ready[2] = {nullptr, nullptr};
+    cudaEvent_t ready[2] = {nullptr, nullptr};   // end of the cloud's outstanding work on its aux stream
+    cudaEvent_t built[2] = {nullptr, nullptr};   // end of its index build (the non-finite flag has been copied back)
     cudaEvent_t fork_ev = nullptr;
 
     // loop state
