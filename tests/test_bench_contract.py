@@ -45,3 +45,12 @@ def test_default_arm_fails_loudly_without_a_gpu():
                          capture_output=True, text=True, timeout=300, cwd=ROOT)
     assert out.returncode != 0
     assert "reference" not in out.stdout
+
+
+def test_pipelined_e2e_is_an_extra_not_the_headline():
+    """`e2e.value` stays the strictly serial call (upload, index, normals, loop, read-back, one registration at a time);
+    the stream of registrations over two contexts is reported beside it under `e2e.pipelined`"""
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    assert '"e2e": {"value": tot_e2e_corr / (max_e2e_ms * 1e-3)' in src
+    assert '"pipelined": None if pipe_ms is None else' in src
+    assert src.index("my_e2e_ms = float(np.sum(e2e_ms))") > src.index("pipe_ms = pe0.elapsed_time(pe1) / k_pipe")   # separate clocks
